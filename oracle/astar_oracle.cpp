@@ -147,7 +147,7 @@ static bool lookahead(Problem& pb, Node& secondary_root);
 static void generate_successors(Problem& pb, const Node& node, std::vector<Node>& out) {
     const Config& cfg = pb.cfg;
     const Id& id = node.id;
-    const i64 LF = cfg.c->left_flank_length, RF = cfg.c->right_flank_length;
+    const i64 LF = cfg.c->left_flank_length;
     switch (id.type) {
     case PRIMARY:
     case PRIMARY_REENTRY: {
@@ -530,9 +530,9 @@ extern "C" int tsao_astar_align(const tsao_config* c, const uint8_t* reference, 
 }
 
 // template_switch_specifics.rs:591-835 (flat iteration clamps non-repeatable ops to multiplicity 1: iter.rs:62-90)
-extern "C" uint64_t tsao_rescore(const tsao_config* c, const uint8_t* R, int64_t n, const uint8_t* Q, int64_t m,
-                                 int64_t ro, int64_t qo, const tsao_op* ops, int64_t n_ops,
-                                 int64_t* end_ref, int64_t* end_qry, int32_t* ok) {
+extern "C" uint64_t tsao_rescore_mode(const tsao_config* c, const uint8_t* R, int64_t n, const uint8_t* Q, int64_t m,
+                                      int64_t ro, int64_t qo, const tsao_op* ops, int64_t n_ops,
+                                      int64_t* end_ref, int64_t* end_qry, int32_t* ok, int32_t as_searched) {
     Config cfg; cfg.c = c; cfg.A = c->alphabet_size; cfg.min_length = 0;
     u64 cost = 0;
     int last = -1, last_group = -1;
@@ -605,6 +605,15 @@ extern "C" uint64_t tsao_rescore(const tsao_config* c, const uint8_t* R, int64_t
             case TSAO_OP_TS_ENTRANCE: {
                 p = op.primary; s = op.secondary; d = op.direction;
                 inc = checked_add(cfg.base(p, s, d), cfg.fn(cfg.offset_fn(p, s), op.value));
+                if (as_searched && d == 0) {
+                    // The search charges a forward entrance oc(0) and then walks from offset +-1
+                    // (identifier.rs:290-319, context.rs:392-462): oc(0) + oc(o) - oc(+-1).  compute_cost charges
+                    // oc(o); the two agree whenever oc is flat around 0 (all shipped configs).
+                    int fnk = cfg.offset_fn(p, s);
+                    i64 sign = op.value < 0 ? -1 : 1;
+                    u64 walk = (op.value == sign) ? 0 : cfg.fn(fnk, op.value) - cfg.fn(fnk, sign);
+                    inc = checked_add(cfg.base(p, s, d), checked_add(cfg.fn(fnk, 0), walk));
+                }
                 if (inc == INF) { *ok = 1; return INF; }
                 pi = p == 0 ? ri : qi;
                 si = (s == 0 ? ri : qi) + op.value;
@@ -635,6 +644,12 @@ extern "C" uint64_t tsao_rescore(const tsao_config* c, const uint8_t* R, int64_t
     if (end_ref) *end_ref = ri;
     if (end_qry) *end_qry = qi;
     return cost;
+}
+
+extern "C" uint64_t tsao_rescore(const tsao_config* c, const uint8_t* R, int64_t n, const uint8_t* Q, int64_t m,
+                                 int64_t ro, int64_t qo, const tsao_op* ops, int64_t n_ops,
+                                 int64_t* end_ref, int64_t* end_qry, int32_t* ok) {
+    return tsao_rescore_mode(c, R, n, Q, m, ro, qo, ops, n_ops, end_ref, end_qry, ok, 0);
 }
 
 extern "C" void tsao_result_free(tsao_result* r) {

@@ -79,6 +79,8 @@ def lib():
         _LIB.tsao_rescore.argtypes = [C.POINTER(_CConfig), C.c_char_p, C.c_int64, C.c_char_p, C.c_int64,
                                       C.c_int64, C.c_int64, C.POINTER(_COp), C.c_int64,
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+        _LIB.tsao_rescore_mode.restype = C.c_uint64
+        _LIB.tsao_rescore_mode.argtypes = _LIB.tsao_rescore.argtypes + [C.c_int32]
         _LIB.tsao_result_free.argtypes = [C.POINTER(_CResult)]
     return _LIB
 
@@ -209,8 +211,8 @@ def dp_align(flat, reference, query, rng=None, **kw):
     return _run(lib().tsao_dp_align, flat, reference, query, rng, **kw)
 
 
-def rescore(flat, reference, query, ops, ref_offset=0, qry_offset=0):
-    """compute_cost restatement. Returns (cost, end_ref, end_qry, ok)."""
+def rescore(flat, reference, query, ops, ref_offset=0, qry_offset=0, as_searched=False):
+    """compute_cost restatement. Returns (cost, end_ref, end_qry, ok).  as_searched: see tsa_oracle.h."""
     a = flat.cfg.alphabet
     r = alphabets.encode(a, reference)
     q = alphabets.encode(a, query)
@@ -218,6 +220,6 @@ def rescore(flat, reference, query, ops, ref_offset=0, qry_offset=0):
     for i, op in enumerate(ops):
         arr[i] = _COp(op.count, op.type, op.primary, op.secondary, op.direction, op.value)
     er, eq, ok = C.c_int64(), C.c_int64(), C.c_int32()
-    cost = lib().tsao_rescore(C.byref(flat.c), r, len(r), q, len(q), ref_offset, qry_offset, arr, len(ops),
-                              C.byref(er), C.byref(eq), C.byref(ok))
+    cost = lib().tsao_rescore_mode(C.byref(flat.c), r, len(r), q, len(q), ref_offset, qry_offset, arr, len(ops),
+                                   C.byref(er), C.byref(eq), C.byref(ok), int(as_searched))
     return cost, er.value, eq.value, bool(ok.value)

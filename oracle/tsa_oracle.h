@@ -12,7 +12,7 @@
  * (tests/test_oracle_kat.py): lib_tsalign/src/tests.rs:38-194 (cost 10),
  * a_star_aligner/tests.rs:10-29 (1D2=2I, cost 9), the compute_cost vectors of
  * alignment_result/alignment/template_switch_specifics.rs:863-1410 and the
- * golden test_files/*.toml (rescoring to the recorded cost).
+ * golden test_files .toml files (rescoring to the recorded cost).
  */
 #ifndef TSA_ORACLE_H
 #define TSA_ORACLE_H
@@ -98,6 +98,12 @@ int tsao_astar_align(const tsao_config* cfg, const uint8_t* reference, int64_t n
 uint64_t tsao_rescore(const tsao_config* cfg, const uint8_t* reference, int64_t n, const uint8_t* query, int64_t m,
                       int64_t ref_offset, int64_t qry_offset, const tsao_op* ops, int64_t n_ops,
                       int64_t* end_ref, int64_t* end_qry, int32_t* ok);
+
+/* Same walk; as_searched != 0 charges forward entrances the way the search does (oc(0) + oc(o) - oc(+-1),
+ * identifier.rs:290-319 + context.rs:392-462) instead of compute_cost's oc(o).  Identical for flat offset costs. */
+uint64_t tsao_rescore_mode(const tsao_config* cfg, const uint8_t* reference, int64_t n, const uint8_t* query, int64_t m,
+                           int64_t ref_offset, int64_t qry_offset, const tsao_op* ops, int64_t n_ops,
+                           int64_t* end_ref, int64_t* end_qry, int32_t* ok, int32_t as_searched);
 
 /* Scalar layered-DP statement of the same shortest-path problem;
  * the thing the CUDA kernels are diffed against at sizes A* cannot reach. */
