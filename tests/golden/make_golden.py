@@ -142,9 +142,8 @@ def main():
     kats["compute_cost"] = {
         "source": "lib_tsalign/src/a_star_aligner/alignment_result/alignment/template_switch_specifics.rs:863-1410",
         "config": cc_cfg,
-        "offsets": [2, 2],
-        "start": {"reference": "AGAGAGCTCTAA", "query": "AGAGAGCTTTAA", "vectors": [{"alignment": a, "cost": c} for a, c in start]},
-        "end": {"reference": "AACTCTAGAGAG", "query": "AATTCTAGAGAG", "vectors": [{"alignment": a, "cost": c} for a, c in end]},
+        "start": {"offsets": [2, 2], "reference": "AGAGAGCTCTAA", "query": "AGAGAGCTTTAA", "vectors": [{"alignment": a, "cost": c} for a, c in start]},
+        "end": {"offsets": [1, 1], "reference": "AACTCTAGAGAG", "query": "AATTCTAGAGAG", "vectors": [{"alignment": a, "cost": c} for a, c in end]},
     }
     kats["cli_smoke"] = {
         "source": "tsalign-tests/tests/integration.rs:6-29",

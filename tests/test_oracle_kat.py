@@ -52,7 +52,7 @@ def test_compute_cost_vectors(kats, which):
     blk = k[which]
     for v in blk["vectors"]:
         ops = ops_from_json(v["alignment"])
-        cost, er, eq, ok = oracle.rescore(flat, blk["reference"], blk["query"], ops, *k["offsets"])
+        cost, er, eq, ok = oracle.rescore(flat, blk["reference"], blk["query"], ops, *blk["offsets"])
         assert ok and cost == v["cost"], (v, cost)
 
 
