@@ -1,0 +1,127 @@
+/*
+ * tsalign_b200.h -- C ABI of the B200-native template-switch aligner (libtsalign_b200.so).
+ *
+ * Drop-in boundary for the alignment hot path of sebschmi/template-switch-aligner.  The reference has no
+ * FFI; its seam is the Rust generic function
+ *     lib_tsalign::a_star_aligner::template_switch_distance_a_star_align   (lib_tsalign/src/a_star_aligner.rs:179-254)
+ * called by the `tsalign align` CLI (tsalign/src/align/template_switch_distance_type_selectors.rs:389-450) and by
+ * the run-time facade lib_tsalign::a_star_aligner::configurable_a_star_align::Aligner::align
+ * (configurable_a_star_align.rs:214-236) used by the Python binding (python_bindings/src/lib.rs:97-142).
+ * Each entry point below names the reference interface it replaces.  INTEGRATION.md shows the Rust `extern "C"`
+ * block and the call-site change a maintainer would add.
+ *
+ * Ownership: the caller owns every input for the duration of a call; results are allocated by the library and
+ * released with tsa_results_free.  No function throws or aborts across the ABI on bad input: integer status codes
+ * plus a message buffer.  There is no CPU path: without a CUDA device every compute entry returns
+ * TSA_ERR_NO_DEVICE.
+ */
+#ifndef TSALIGN_B200_H
+#define TSALIGN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes --------------------------------------------------------------------------------------- */
+enum {
+    TSA_OK = 0,
+    TSA_ERR_NO_DEVICE = 1,          /* no CUDA device / invalid device index */
+    TSA_ERR_CONFIG_PARSE = 2,       /* lib_tsalign/src/error.rs: Error::Parser* */
+    TSA_ERR_NOT_V_SHAPED_RQQR = 3,  /* error.rs: RQQROffsetCostsNotVShaped (config.rs:72-85) */
+    TSA_ERR_NOT_V_SHAPED_RRQQ = 4,  /* error.rs: RRQQOffsetCostsNotVShaped */
+    TSA_ERR_NOT_V_SHAPED_LENDIFF = 5, /* error.rs: LengthDifferenceCostsNotVShaped */
+    TSA_ERR_ALPHABET = 6,           /* unknown alphabet id */
+    TSA_ERR_INVALID_CHAR = 7,       /* a sequence character is not in the alphabet (align.rs:389-405; the facade panics) */
+    TSA_ERR_INVALID_RANGE = 8,      /* offset > limit or limit > length */
+    TSA_ERR_UNSUPPORTED = 9,        /* cost model outside the kernels' limits (see message) */
+    TSA_ERR_ARGUMENT = 10
+};
+
+/* ---- alphabets: tsalign/src/align.rs:80-81,288-295 (-a/--alphabet) -------------------------------------- */
+enum { TSA_ALPHABET_DNA = 0, TSA_ALPHABET_DNA_N = 1, TSA_ALPHABET_RNA = 2, TSA_ALPHABET_RNA_N = 3, TSA_ALPHABET_DNA_IUPAC = 4, TSA_ALPHABET_RNA_IUPAC = 5 };
+
+/* ---- cost model: lib_tsalign::config::TemplateSwitchConfig (config.rs:24-49) ---------------------------- */
+typedef struct tsa_config tsa_config;
+
+/* TemplateSwitchConfig::read_plain / from_str (config/io.rs:21-31,265-275): parse a config.tsa text. */
+tsa_config* tsa_config_parse(const char* text, size_t len, int alphabet, int* status, char* err, size_t errcap);
+/* TemplateSwitchConfig::default() (config.rs:219-303): the cost model the Python binding uses when none is given. */
+tsa_config* tsa_config_default(int alphabet);
+/* Display for TemplateSwitchConfig (config/io.rs:223-263): config.tsa text; returns the needed size incl. NUL. */
+size_t tsa_config_write(const tsa_config* cfg, char* out, size_t cap);
+void tsa_config_free(tsa_config* cfg);
+int tsa_config_alphabet(const tsa_config* cfg);
+
+/* ---- options: the result-relevant part of the strategy selection (align.rs:104-223) --------------------- */
+typedef struct {
+    int32_t no_ts;                 /* --no-ts (MaxTemplateSwitchCount(0)) */
+    int32_t device;                /* CUDA device index */
+    uint64_t cost_limit;           /* --cost-limit, UINT64_MAX = none: optimal cost > limit -> ExceededCostLimit */
+    uint64_t memory_limit;         /* --memory-limit in bytes, UINT64_MAX = none: bounds the resident HBM chunk */
+    int32_t max_template_switches; /* 0 = default (64) */
+    int32_t reserved;
+} tsa_options;
+
+/* ---- one alignment problem: the arguments of Aligner::align (configurable_a_star_align.rs:214-236) ------ */
+typedef struct {
+    const char* reference; size_t reference_len;   /* ASCII, already upper-cased / skip characters removed */
+    const char* query; size_t query_len;
+    int64_t reference_offset, reference_limit;     /* AlignmentRange; limit < 0 means "end of sequence" */
+    int64_t query_offset, query_limit;
+} tsa_pair;
+
+/* ---- result: generic_a_star::AStarResult (generic_a_star/src/lib.rs:164-187) + alignment ---------------- */
+enum { TSA_FOUND_TARGET = 0, TSA_EXCEEDED_COST_LIMIT = 1, TSA_EXCEEDED_MEMORY_LIMIT = 2, TSA_NO_TARGET = 3 };
+
+/* AlignmentType (template_switch_distance/alignment_type.rs:11-75) */
+enum {
+    TSA_OP_PRIMARY_INSERTION = 0, TSA_OP_PRIMARY_DELETION = 1, TSA_OP_PRIMARY_SUBSTITUTION = 2, TSA_OP_PRIMARY_MATCH = 3,
+    TSA_OP_PRIMARY_FLANK_INSERTION = 4, TSA_OP_PRIMARY_FLANK_DELETION = 5, TSA_OP_PRIMARY_FLANK_SUBSTITUTION = 6, TSA_OP_PRIMARY_FLANK_MATCH = 7,
+    TSA_OP_SECONDARY_INSERTION = 8, TSA_OP_SECONDARY_DELETION = 9, TSA_OP_SECONDARY_SUBSTITUTION = 10, TSA_OP_SECONDARY_MATCH = 11,
+    TSA_OP_TS_ENTRANCE = 12, TSA_OP_TS_EXIT = 13
+};
+
+typedef struct {
+    int64_t count;       /* run length as the reference emits it (a_star_aligner.rs:100-122) */
+    int32_t type;        /* TSA_OP_* */
+    int32_t primary;     /* entrance: 0 = Reference, 1 = Query */
+    int32_t secondary;   /* entrance */
+    int32_t direction;   /* entrance: 0 = Forward, 1 = Reverse */
+    int64_t value;       /* entrance: first_offset; exit: anti_primary_gap */
+} tsa_op;
+
+typedef struct {
+    int32_t status;            /* TSA_OK or a per-pair TSA_ERR_* */
+    int32_t result_type;       /* TSA_FOUND_TARGET ... */
+    uint64_t cost;             /* FoundTarget: cost; ExceededCostLimit: the limit */
+    int32_t template_switches; /* number of template switches on the returned path */
+    int32_t reserved;
+    tsa_op* ops;               /* run-length encoded alignment (NULL when no alignment was requested / found) */
+    size_t n_ops;
+    double duration_seconds;   /* share of the batch's wall time */
+    char message[96];          /* human-readable reason when status != TSA_OK */
+} tsa_result;
+
+/* Batch form of template_switch_distance_a_star_align: aligns n independent pairs on one GPU. */
+int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pairs, size_t n, tsa_result* out, char* err, size_t errcap);
+void tsa_results_free(tsa_result* results, size_t n);
+
+/* ---- staged form (what bench.py times): inputs resident in HBM, run any number of times ------------------ */
+typedef struct tsa_batch tsa_batch;
+tsa_batch* tsa_batch_create(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pairs, size_t n, int* status, char* err, size_t errcap);
+int tsa_batch_run(tsa_batch* batch);                              /* kernels only; synchronous */
+int tsa_batch_fetch(tsa_batch* batch, tsa_result* out);           /* D2H + result assembly */
+void tsa_batch_stats(const tsa_batch* batch, int64_t* launches, int64_t* jump_launches, int64_t* fill_launches, int32_t* layers, int64_t* h2d_bytes, int64_t* d2h_bytes);
+void tsa_batch_free(tsa_batch* batch);
+
+/* ---- misc ----------------------------------------------------------------------------------------------- */
+int tsa_device_count(void);
+const char* tsa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,318 @@
+"""Host-side mirror of the reference's Python surface (python_bindings/python/tsalign/__init__.py:33-249,
+_types.py:7-73) on top of the C ABI: `Aligner`, `align`, `Alignment`, `AlignmentRange`, the op dataclasses --
+plus the batch entry points the GPU path is built for (`Aligner.align_batch`, `StagedBatch`)."""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple, Union
+
+from . import _lib
+from ._lib import TsaError, TsaOp, TsaOptions, TsaPair, TsaResult, U64_MAX
+
+_ALIGNER_KWARG_NAMES = frozenset({"no_ts", "min_length_strategy", "chaining_strategy", "total_length_strategy", "costs", "costs_file"})
+_MIN_LENGTH = {"none", "lookahead", "preprocess_price", "preprocess_filter", "preprocess_lookahead"}
+_CHAINING = {"none", "lower_bound"}
+_TOTAL_LENGTH = {"none", "maximise"}
+
+
+@dataclass
+class AlignmentRange:
+    """Coordinate bounds for a pairwise alignment (_types.py:7-14)."""
+    reference_start: int = 0
+    reference_end: "int | None" = None
+    query_start: int = 0
+    query_end: "int | None" = None
+
+
+@dataclass
+class SimpleAlignmentOp:
+    kind: str
+
+
+@dataclass
+class TemplateSwitchEntranceOp:
+    kind: str
+    first_offset: int
+    primary: str
+    secondary: str
+    direction: str
+    equal_cost_range: dict
+
+
+@dataclass
+class TemplateSwitchExitOp:
+    kind: str
+    anti_primary_gap: int
+
+
+AlignmentOp = Union[SimpleAlignmentOp, TemplateSwitchEntranceOp, TemplateSwitchExitOp]
+_INVALID_RANGE = {"min_start": 127, "max_start": -128, "min_end": 127, "max_end": -128}
+
+
+class Config:
+    """A parsed cost model (lib_tsalign::config::TemplateSwitchConfig)."""
+
+    def __init__(self, text: Optional[str] = None, alphabet: str = "dna-n", lib=None):
+        self._lib = lib or _lib.default()
+        if alphabet not in _lib.ALPHABETS:
+            raise ValueError(f"unknown alphabet {alphabet!r}")
+        self.alphabet = alphabet
+        if text is None:
+            self._h = self._lib.tsa_config_default(_lib.ALPHABETS[alphabet])
+            if not self._h:
+                raise TsaError(6, "unknown alphabet")
+        else:
+            status = C.c_int(0)
+            err = C.create_string_buffer(512)
+            raw = text.encode()
+            self._h = self._lib.tsa_config_parse(raw, len(raw), _lib.ALPHABETS[alphabet], C.byref(status), err, len(err))
+            if not self._h:
+                raise TsaError(status.value, err.value.decode(errors="replace"))
+
+    def text(self) -> str:
+        n = self._lib.tsa_config_write(self._h, None, 0)
+        buf = C.create_string_buffer(n)
+        self._lib.tsa_config_write(self._h, buf, n)
+        return buf.value.decode()
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.tsa_config_free(h)
+
+
+def _clean(seq) -> bytes:
+    # python_bindings/src/lib.rs:53-56: str(obj).encode()
+    return seq if isinstance(seq, bytes) else str(seq).encode()
+
+
+def _make_pairs(pairs: Sequence[tuple]):
+    """[(reference, query) | (reference, query, (ro, rl, qo, ql))] -> (TsaPair array, keep-alive list)."""
+    arr = (TsaPair * max(1, len(pairs)))()
+    keep = []
+    for i, p in enumerate(pairs):
+        r, q = _clean(p[0]), _clean(p[1])
+        rng = p[2] if len(p) > 2 and p[2] is not None else (0, None, 0, None)
+        keep.append((r, q))
+        arr[i].reference, arr[i].reference_len = r, len(r)
+        arr[i].query, arr[i].query_len = q, len(q)
+        arr[i].reference_offset = rng[0] or 0
+        arr[i].reference_limit = -1 if rng[1] is None else rng[1]
+        arr[i].query_offset = rng[2] or 0
+        arr[i].query_limit = -1 if rng[3] is None else rng[3]
+    return arr, keep
+
+
+def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0) -> TsaOptions:
+    o = TsaOptions()
+    o.no_ts = int(bool(no_ts))
+    o.device = device
+    o.cost_limit = U64_MAX if cost_limit is None else int(cost_limit)
+    o.memory_limit = U64_MAX if memory_limit is None else int(memory_limit)
+    o.max_template_switches = max_template_switches
+    return o
+
+
+@dataclass
+class BatchResult:
+    """One entry of a batch: the C struct tsa_result, copied out."""
+    status: int
+    result_type: str
+    cost: int
+    template_switches: int
+    ops: Optional[List[Tuple[int, int, int, int, int, int]]]  # (count, type, primary, secondary, direction, value)
+    message: str = ""
+    duration_seconds: float = 0.0
+
+    @property
+    def found(self) -> bool:
+        return self.status == 0 and self.result_type == "FoundTarget"
+
+
+def _copy_results(lib, res, n) -> List[BatchResult]:
+    out = []
+    for i in range(n):
+        r = res[i]
+        ops = None
+        if r.ops:
+            ops = [(r.ops[k].count, r.ops[k].type, r.ops[k].primary, r.ops[k].secondary, r.ops[k].direction, r.ops[k].value) for k in range(r.n_ops)]
+        out.append(BatchResult(r.status, _lib.RESULT_NAMES[r.result_type], r.cost, r.template_switches, ops,
+                               r.message.decode(errors="replace"), r.duration_seconds))
+    lib.tsa_results_free(res, n)
+    return out
+
+
+def cigar_of(ops) -> str:
+    """Alignment::cigar (alignment.rs:95-110, template_switch_distance/display.rs:8-41); equal-cost ranges invalid."""
+    out = []
+    for count, t, p, s, d, v in ops:
+        if t == 12:
+            out.append("[TS%s%s%s:[-]:[-]:%d:" % ("RQ"[p], "RQ"[s], "FR"[d], v))
+        elif t == 13:
+            out.append(":%d]" % v)
+        else:
+            out.append("%d%s" % (count, "IDX="[t & 3]))
+    return "".join(out)
+
+
+class Alignment:
+    """Result of one pairwise alignment (mirror of tsalign.Alignment)."""
+
+    def __init__(self, result: BatchResult, reference: bytes, query: bytes, names: Tuple[str, str], rng, alphabet: str):
+        self._r = result
+        self._reference, self._query = reference, query
+        self._names = names
+        self._range = rng
+        self._alphabet = alphabet
+
+    @property
+    def cost(self) -> int:
+        return self._r.cost
+
+    def cigar(self) -> Optional[str]:
+        if not self._r.found or self._r.ops is None:
+            return None
+        return cigar_of(self._r.ops)
+
+    def alignments(self) -> Optional[List[Tuple[int, AlignmentOp]]]:
+        if not self._r.found or self._r.ops is None:
+            return None
+        out = []
+        for count, t, p, s, d, v in self._r.ops:
+            if t == 12:
+                out.append((count, TemplateSwitchEntranceOp("TemplateSwitchEntrance", v, ["Reference", "Query"][p], ["Reference", "Query"][s],
+                                                            ["Forward", "Reverse"][d], dict(_INVALID_RANGE))))
+            elif t == 13:
+                out.append((count, TemplateSwitchExitOp("TemplateSwitchExit", v)))
+            else:
+                out.append((count, SimpleAlignmentOp(_lib.OP_NAMES[t])))
+        return out
+
+    def stats(self) -> dict:
+        """AlignmentStatistics (alignment_result.rs:53-81,194-227); the A* node counters have no meaning for a dense fill."""
+        r = self._r
+        n, m = len(self._reference), len(self._query)
+        ts = sum(1 for op in (r.ops or []) if op[1] == 13)
+        result = {"astar_result_type": r.result_type}
+        if r.result_type == "FoundTarget":
+            result["cost"] = r.cost
+        elif r.result_type == "ExceededCostLimit":
+            result["cost_limit"] = r.cost
+        return {
+            "result": result,
+            "sequences": {"reference_name": self._names[0], "reference": self._reference.decode(), "query_name": self._names[1], "query": self._query.decode()},
+            "reference_offset": self._range[0], "query_offset": self._range[2],
+            "cost": float(r.cost), "cost_per_base": (2.0 * r.cost / (n + m)) if n + m else 0.0,
+            "duration_seconds": r.duration_seconds, "opened_nodes": 0.0, "closed_nodes": 0.0, "suboptimal_opened_nodes": 0.0,
+            "suboptimal_opened_nodes_ratio": 0.0, "template_switch_amount": float(ts), "runtime": 0.0, "memory": 0.0,
+        }
+
+
+class Aligner:
+    """Pairwise sequence aligner with template-switch detection on a B200 (mirror of tsalign.Aligner).
+
+    The search-heuristic arguments of the reference (`min_length_strategy`, `chaining_strategy`) are validated and
+    ignored: they never change the optimal cost.  `total_length_strategy` only affects which of several
+    equal-cost alignments the reference returns; this implementation uses its own documented tie-break.
+    Defaults match the reference: alphabet dna-n, Rust `TemplateSwitchConfig::default()` costs.
+    """
+
+    def __init__(self, *, no_ts: bool = False, min_length_strategy: str = "lookahead", chaining_strategy: str = "none",
+                 total_length_strategy: str = "maximise", costs: Optional[str] = None,
+                 costs_file: Optional[Union[str, pathlib.Path]] = None, alphabet: str = "dna-n", device: int = 0, lib=None) -> None:
+        if costs is not None and costs_file is not None:
+            raise ValueError("Provide at most one of 'costs' or 'costs_file'.")
+        if min_length_strategy not in _MIN_LENGTH:
+            raise ValueError(f"unknown min_length_strategy {min_length_strategy!r}")
+        if chaining_strategy not in _CHAINING:
+            raise ValueError(f"unknown chaining_strategy {chaining_strategy!r}")
+        if total_length_strategy not in _TOTAL_LENGTH:
+            raise ValueError(f"unknown total_length_strategy {total_length_strategy!r}")
+        if costs_file is not None:
+            costs = pathlib.Path(costs_file).read_text()
+        self._lib = lib or _lib.default()
+        self.no_ts = bool(no_ts)
+        self.device = device
+        self.config = Config(costs, alphabet, lib=self._lib)
+
+    # -- batch entry point: the call the GPU path is built for ----------------------------------------------
+    def align_batch(self, pairs: Sequence[tuple], *, cost_limit: Optional[int] = None, memory_limit: Optional[int] = None) -> List[BatchResult]:
+        """Align independent pairs: [(reference, query) or (reference, query, (ref_offset, ref_limit, qry_offset, qry_limit))]."""
+        arr, keep = _make_pairs(pairs)
+        res = (TsaResult * max(1, len(pairs)))()
+        err = C.create_string_buffer(512)
+        opt = _options(self.no_ts, self.device, cost_limit, memory_limit)
+        rc = self._lib.tsa_align_batch(self.config._h, C.byref(opt), arr, len(pairs), res, err, len(err))
+        if rc != 0:
+            raise TsaError(rc, err.value.decode(errors="replace"))
+        del keep
+        return _copy_results(self._lib, res, len(pairs))
+
+    def align(self, reference: object, query: object, *, reference_name: str = "reference", query_name: str = "query",
+              range: Optional[AlignmentRange] = None, reference_start: Optional[int] = None, reference_limit: Optional[int] = None,
+              query_start: Optional[int] = None, query_limit: Optional[int] = None, cost_limit: Optional[int] = None,
+              memory_limit: Optional[int] = None) -> Optional[Alignment]:
+        """Align two sequences.  Returns None when no target was found within the limits (lib.rs:135-141)."""
+        if range is not None:
+            reference_start, reference_limit = range.reference_start, range.reference_end
+            query_start, query_limit = range.query_start, range.query_end
+        r, q = _clean(reference), _clean(query)
+        rng = (reference_start or 0, reference_limit, query_start or 0, query_limit)
+        res = self.align_batch([(r, q, rng)], cost_limit=cost_limit, memory_limit=memory_limit)[0]
+        if res.status != 0:
+            raise TsaError(res.status, res.message)
+        if not res.found:
+            return None
+        full = (rng[0], len(r) if rng[1] is None else rng[1], rng[2], len(q) if rng[3] is None else rng[3])
+        return Alignment(res, r, q, (reference_name, query_name), full, self.config.alphabet)
+
+
+def align(reference: object, query: object, **kwargs: object) -> Optional[Alignment]:
+    """One-call convenience wrapper (mirror of tsalign.align)."""
+    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib")}
+    align_kwargs = {k: v for k, v in kwargs.items() if k not in aligner_kwargs}
+    return Aligner(**aligner_kwargs).align(reference, query, **align_kwargs)
+
+
+class StagedBatch:
+    """Inputs resident in HBM; `run()` executes the kernels only (what bench.py times as `value`)."""
+
+    def __init__(self, aligner: Aligner, pairs: Sequence[tuple], *, cost_limit=None, memory_limit=None):
+        self._lib = aligner._lib
+        self._aligner = aligner
+        self.n = len(pairs)
+        arr, keep = _make_pairs(pairs)
+        status = C.c_int(0)
+        err = C.create_string_buffer(512)
+        opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit)
+        self._h = self._lib.tsa_batch_create(aligner.config._h, C.byref(opt), arr, self.n, C.byref(status), err, len(err))
+        if not self._h:
+            raise TsaError(status.value, err.value.decode(errors="replace"))
+
+    def run(self) -> None:
+        rc = self._lib.tsa_batch_run(self._h)
+        if rc != 0:
+            raise TsaError(rc, "tsa_batch_run")
+
+    def fetch(self) -> List[BatchResult]:
+        res = (TsaResult * max(1, self.n))()
+        rc = self._lib.tsa_batch_fetch(self._h, res)
+        if rc != 0:
+            raise TsaError(rc, "tsa_batch_fetch")
+        return _copy_results(self._lib, res, self.n)
+
+    def stats(self) -> dict:
+        a, b, c, e, f = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        d = C.c_int32()
+        self._lib.tsa_batch_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e), C.byref(f))
+        return {"launches": a.value, "jump_launches": b.value, "fill_launches": c.value, "layers": d.value, "h2d_bytes": e.value, "d2h_bytes": f.value}
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.tsa_batch_free(h)
+
+    def __del__(self):
+        self.close()

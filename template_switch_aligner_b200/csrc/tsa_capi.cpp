@@ -1,0 +1,255 @@
+// tsa_capi.cpp -- the extern "C" boundary declared in include/tsalign_b200.h.
+#include "tsalign_b200.h"
+
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "tsa_config.hpp"
+#include "tsa_engine.hpp"
+#include "tsa_rt.hpp"
+
+using namespace tsa;
+
+struct tsa_config {
+    HostConfig host;
+};
+
+namespace {
+
+void set_err(char* err, size_t cap, const std::string& msg) {
+    if (!err || cap == 0) return;
+    size_t n = std::min(cap - 1, msg.size());
+    memcpy(err, msg.data(), n);
+    err[n] = '\0';
+}
+
+struct Encoded {
+    std::vector<uint8_t> pool;
+    std::vector<PairView> views;
+    std::vector<int> pair_status;       // TSA_OK or per-pair input error
+    std::vector<std::string> pair_msg;
+    std::vector<size_t> live;           // indices of pairs handed to the engine
+};
+
+// tsalign/src/align.rs:389-405 (VectorGenome::from_slice_u8) + AlignmentRange checks.
+void encode_pairs(const HostConfig& cfg, const tsa_pair* pairs, size_t n, Encoded& e) {
+    int lut[256];
+    for (int c = 0; c < 256; c++) lut[c] = alphabet_index(cfg.alphabet, (unsigned char)c);
+    size_t total = 0;
+    for (size_t i = 0; i < n; i++) total += pairs[i].reference_len + pairs[i].query_len;
+    e.pool.resize(total + 1);
+    e.pair_status.assign(n, TSA_OK);
+    e.pair_msg.assign(n, std::string());
+    size_t off = 0;
+    std::vector<PairView> all(n);
+    for (size_t i = 0; i < n; i++) {
+        const tsa_pair& p = pairs[i];
+        PairView v;
+        v.ref = &e.pool[off];
+        for (size_t k = 0; k < p.reference_len; k++) {
+            int x = lut[(unsigned char)p.reference[k]];
+            if (x < 0 && e.pair_status[i] == TSA_OK) { e.pair_status[i] = TSA_ERR_INVALID_CHAR; e.pair_msg[i] = std::string("reference character '") + p.reference[k] + "' is not part of alphabet " + alphabet_name(cfg.alphabet); }
+            e.pool[off++] = (uint8_t)(x < 0 ? 0 : x);
+        }
+        v.qry = &e.pool[off];
+        for (size_t k = 0; k < p.query_len; k++) {
+            int x = lut[(unsigned char)p.query[k]];
+            if (x < 0 && e.pair_status[i] == TSA_OK) { e.pair_status[i] = TSA_ERR_INVALID_CHAR; e.pair_msg[i] = std::string("query character '") + p.query[k] + "' is not part of alphabet " + alphabet_name(cfg.alphabet); }
+            e.pool[off++] = (uint8_t)(x < 0 ? 0 : x);
+        }
+        v.n = (int)p.reference_len; v.m = (int)p.query_len;
+        int64_t rl = p.reference_limit < 0 ? (int64_t)p.reference_len : p.reference_limit;
+        int64_t ql = p.query_limit < 0 ? (int64_t)p.query_len : p.query_limit;
+        if (e.pair_status[i] == TSA_OK && (p.reference_offset < 0 || p.query_offset < 0 || p.reference_offset > rl || p.query_offset > ql ||
+                                           rl > (int64_t)p.reference_len || ql > (int64_t)p.query_len)) {
+            e.pair_status[i] = TSA_ERR_INVALID_RANGE; e.pair_msg[i] = "alignment range outside the sequences";
+        }
+        if (e.pair_status[i] == TSA_OK && (p.reference_len > (size_t)1 << 30 || p.query_len > (size_t)1 << 30)) { e.pair_status[i] = TSA_ERR_UNSUPPORTED; e.pair_msg[i] = "sequence too long"; }
+        v.ro = (int)p.reference_offset; v.rl = (int)rl; v.qo = (int)p.query_offset; v.ql = (int)ql;
+        all[i] = v;
+    }
+    for (size_t i = 0; i < n; i++) if (e.pair_status[i] == TSA_OK) { e.live.push_back(i); e.views.push_back(all[i]); }
+}
+
+void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
+    memset(&r, 0, sizeof(r));
+    switch (pc.status) {
+    case PAIR_OK:
+        r.status = TSA_OK;
+        if (opt.cost_limit != UINT64_MAX && (uint64_t)pc.cost > opt.cost_limit) {
+            // generic_a_star/src/lib.rs:372-377,654-660: with an exact fill, "f > limit" means "optimum > limit"
+            r.result_type = TSA_EXCEEDED_COST_LIMIT; r.cost = opt.cost_limit;
+        } else {
+            r.result_type = TSA_FOUND_TARGET; r.cost = (uint64_t)pc.cost; r.template_switches = pc.layers;
+        }
+        break;
+    case PAIR_NO_TARGET: r.status = TSA_OK; r.result_type = TSA_NO_TARGET; break;
+    case PAIR_ERR_TOO_LONG: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "template switches need sequences of at most 1055 characters in this build"); break;
+    case PAIR_ERR_COST_RANGE: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "alignment cost exceeds the 16-bit lanes of the template-switch kernel"); break;
+    case PAIR_ERR_LAYER_CAP: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "more template switches than max_template_switches still improve the cost"); break;
+    case PAIR_ERR_FLANKS: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "flank lengths > 0 with template switches are not built yet"); break;
+    default: r.status = TSA_ERR_ARGUMENT; break;
+    }
+}
+
+AlignOptions engine_options(const tsa_options& o) {
+    AlignOptions a;
+    a.no_ts = o.no_ts != 0;
+    if (o.max_template_switches > 0) a.max_layers = o.max_template_switches;
+    if (o.memory_limit != UINT64_MAX) a.chunk_bytes = (size_t)std::max<uint64_t>(o.memory_limit, (uint64_t)1 << 20);
+    return a;
+}
+
+tsa_options default_options() {
+    tsa_options o;
+    memset(&o, 0, sizeof(o));
+    o.cost_limit = UINT64_MAX; o.memory_limit = UINT64_MAX;
+    return o;
+}
+
+}  // namespace
+
+extern "C" {
+
+tsa_config* tsa_config_parse(const char* text, size_t len, int alphabet, int* status, char* err, size_t errcap) {
+    std::unique_ptr<tsa_config> cfg(new tsa_config);
+    std::string msg;
+    int rc = parse_config(std::string(text ? text : "", text ? len : 0), alphabet, cfg->host, msg);
+    static const int map[] = {TSA_OK, TSA_ERR_CONFIG_PARSE, TSA_ERR_NOT_V_SHAPED_RQQR, TSA_ERR_NOT_V_SHAPED_RRQQ, TSA_ERR_NOT_V_SHAPED_LENDIFF, TSA_ERR_ALPHABET};
+    if (status) *status = map[rc];
+    if (rc != CFG_OK) { set_err(err, errcap, msg); return nullptr; }
+    return cfg.release();
+}
+
+tsa_config* tsa_config_default(int alphabet) {
+    if (alphabet < 0 || alphabet >= ALPHA_COUNT) return nullptr;
+    tsa_config* cfg = new tsa_config;
+    cfg->host = default_config(alphabet);
+    return cfg;
+}
+
+size_t tsa_config_write(const tsa_config* cfg, char* out, size_t cap) {
+    if (!cfg) return 0;
+    std::string s = write_config(cfg->host);
+    if (out && cap) { size_t n = std::min(cap - 1, s.size()); memcpy(out, s.data(), n); out[n] = '\0'; }
+    return s.size() + 1;
+}
+
+void tsa_config_free(tsa_config* cfg) { delete cfg; }
+int tsa_config_alphabet(const tsa_config* cfg) { return cfg ? cfg->host.alphabet : -1; }
+
+}  // extern "C"
+
+struct tsa_batch {
+    std::unique_ptr<Engine> engine;
+    Encoded enc;
+    tsa_options opt;
+    size_t n = 0;
+    std::vector<PairCost> costs;
+};
+
+extern "C" {
+
+tsa_batch* tsa_batch_create(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pairs, size_t n, int* status, char* err, size_t errcap) {
+    int dummy; if (!status) status = &dummy;
+    if (!cfg || (!pairs && n)) { *status = TSA_ERR_ARGUMENT; set_err(err, errcap, "null argument"); return nullptr; }
+    std::unique_ptr<tsa_batch> b(new tsa_batch);
+    b->opt = opt ? *opt : default_options();
+    b->n = n;
+    b->engine.reset(new Engine(cfg->host, b->opt.device));
+    if (!b->engine->ok()) {
+        *status = b->engine->error().find("CUDA") != std::string::npos ? TSA_ERR_NO_DEVICE : TSA_ERR_UNSUPPORTED;
+        set_err(err, errcap, b->engine->error());
+        return nullptr;
+    }
+    encode_pairs(cfg->host, pairs, n, b->enc);
+    AlignOptions ao = engine_options(b->opt);
+    ao.chunk_bytes = std::max(ao.chunk_bytes, (size_t)1 << 40);  // staged form: one resident chunk, caller sizes the batch
+    if (!b->engine->stage(b->enc.views.data(), b->enc.views.size(), ao)) { *status = TSA_ERR_UNSUPPORTED; set_err(err, errcap, "batch does not fit one chunk"); return nullptr; }
+    *status = TSA_OK;
+    return b.release();
+}
+
+int tsa_batch_run(tsa_batch* b) {
+    if (!b) return TSA_ERR_ARGUMENT;
+    b->engine->run_staged();
+    return TSA_OK;
+}
+
+int tsa_batch_fetch(tsa_batch* b, tsa_result* out) {
+    if (!b || !out) return TSA_ERR_ARGUMENT;
+    b->costs.resize(b->enc.views.size());
+    b->engine->fetch_staged(b->costs.data());
+    for (size_t i = 0; i < b->n; i++) {
+        memset(&out[i], 0, sizeof(tsa_result));
+        out[i].status = b->enc.pair_status[i];
+        snprintf(out[i].message, sizeof(out[i].message), "%s", b->enc.pair_msg[i].c_str());
+    }
+    for (size_t k = 0; k < b->enc.live.size(); k++) fill_result(out[b->enc.live[k]], b->costs[k], b->opt);
+    return TSA_OK;
+}
+
+void tsa_batch_stats(const tsa_batch* b, int64_t* launches, int64_t* jump_launches, int64_t* fill_launches, int32_t* layers, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!b) return;
+    const EngineStats& s = b->engine->stats();
+    if (launches) *launches = s.launches;
+    if (jump_launches) *jump_launches = s.jump_launches;
+    if (fill_launches) *fill_launches = s.fill_launches;
+    if (layers) *layers = s.layers_run;
+    if (h2d_bytes) *h2d_bytes = s.h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = s.d2h_bytes;
+}
+
+void tsa_batch_free(tsa_batch* b) { delete b; }
+
+int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pairs, size_t n, tsa_result* out, char* err, size_t errcap) {
+    if (!cfg || (!pairs && n) || (!out && n)) { set_err(err, errcap, "null argument"); return TSA_ERR_ARGUMENT; }
+    const tsa_options o = opt ? *opt : default_options();
+    auto t0 = std::chrono::steady_clock::now();
+    Engine engine(cfg->host, o.device);
+    if (!engine.ok()) {
+        set_err(err, errcap, engine.error());
+        return engine.error().find("CUDA") != std::string::npos ? TSA_ERR_NO_DEVICE : TSA_ERR_UNSUPPORTED;
+    }
+    Encoded enc;
+    encode_pairs(cfg->host, pairs, n, enc);
+    std::vector<PairCost> costs(enc.views.size());
+    engine.align_costs(enc.views.data(), enc.views.size(), engine_options(o), costs.data());
+    for (size_t i = 0; i < n; i++) {
+        memset(&out[i], 0, sizeof(tsa_result));
+        out[i].status = enc.pair_status[i];
+        snprintf(out[i].message, sizeof(out[i].message), "%s", enc.pair_msg[i].c_str());
+    }
+    for (size_t k = 0; k < enc.live.size(); k++) fill_result(out[enc.live[k]], costs[k], o);
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (size_t i = 0; i < n; i++) out[i].duration_seconds = n ? secs / (double)n : 0.0;
+    return TSA_OK;
+}
+
+void tsa_results_free(tsa_result* results, size_t n) {
+    if (!results) return;
+    for (size_t i = 0; i < n; i++) { free(results[i].ops); results[i].ops = nullptr; results[i].n_ops = 0; }
+}
+
+int tsa_device_count(void) {
+#ifndef TSA_EMUL
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+#else
+    return 1;
+#endif
+}
+
+const char* tsa_version(void) {
+#ifndef TSA_EMUL
+    return "tsalign_b200 0.1.0 (sm_100a)";
+#else
+    return "tsalign_b200 0.1.0 (SIMT emulator, tests only)";
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+// tsa_engine.cu -- see tsa_engine.hpp.  Compiled by nvcc for sm_100a (product) or by g++ with -DTSA_EMUL
+// (tests/emul only).
+#include "tsa_engine.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+#include "tsa_kernels.cuh"
+
+namespace tsa {
+
+namespace {
+
+constexpr int N_CLASS = 5;
+const int CLASS_C[N_CLASS] = {3, 5, 9, 17, 33};   // columns per lane of k_ts_jump<C>: 96 .. 1056 columns
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes > cap) { rt::dev_free(p); p = rt::dev_alloc(bytes); cap = bytes; }
+    }
+    ~DevBuf() { rt::dev_free(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+size_t jump_smem_per_warp(int A, int C) {
+    const int LW = 32 * C;
+    int KL = 0;
+    while ((1 << (KL + 1)) <= LW) KL++;
+    KL += 1;
+    const size_t sub_bytes = ((size_t)A * LW * 2 + 15) & ~(size_t)15;
+    return sub_bytes + (size_t)KL * LW * 4;
+}
+
+int jump_warps(int A, int C) {
+    const size_t per = jump_smem_per_warp(A, C);
+    int w = K2_WARPS;
+    while (w > 1 && per * w > (size_t)200 * 1024) w >>= 1;
+    return w;
+}
+
+template <int C>
+void launch_jump(const Chunk& ck, const int* d_list, int n_list, int max_len, int A, int n_kinds, int ml, cudaStream_t stream, long long& launches) {
+    const int warps = jump_warps(A, C);
+    const size_t smem = jump_smem_per_warp(A, C) * warps;
+#ifndef TSA_EMUL
+    static bool attr_set = false;
+    if (!attr_set) {
+        rt::check(cudaFuncSetAttribute(k_ts_jump<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
+        attr_set = true;
+    }
+#endif
+    const int n_ep = (max_len - ml + 2) / 2;
+    if (n_ep <= 0 || n_kinds <= 0) return;
+    const int tasks = n_kinds * n_ep;
+    const unsigned gx = (unsigned)((tasks + warps - 1) / warps);
+    for (int off = 0; off < n_list; off += 65535) {
+        const int cnt = std::min(65535, n_list - off);
+        TSA_LAUNCH(k_ts_jump<C>, dim3(gx, (unsigned)cnt), dim3(32 * warps), smem, stream, ck, d_list + off, cnt);
+        launches++;
+    }
+}
+
+}  // namespace
+
+struct Engine::Impl {
+    int device = 0;
+    cudaStream_t stream = 0;
+    DevBuf cfg, lc, meta, seq, D, DT, seedA, seedB, minvec, scratch, best, best_layer, active, next_active, counters, lists;
+    std::vector<PairMeta> metas;
+    std::vector<uint8_t> seqpool;
+    std::vector<int> status;            // per staged pair (PairStatus)
+    std::vector<int> list_all;          // staged pairs that run at all
+    std::vector<int> class_list[N_CLASS];
+    int class_maxlen[N_CLASS] = {0};
+    int* d_list_all = nullptr;
+    int* d_class_list[N_CLASS] = {nullptr};
+    size_t npairs = 0;
+    AlignOptions opt;
+    Chunk ck;
+    bool ts_enabled = false;
+    std::vector<int> h_best, h_layer, h_active;
+#ifndef TSA_EMUL
+    cudaEvent_t ev[4];
+#endif
+};
+
+size_t Engine::bytes_per_pair(int n, int m) {
+    const size_t cells = (size_t)(n + 1) * (m + 1);
+    return cells * (2 + 2 + 4 + 4) + (size_t)(n + m + 2) * 4 + (size_t)(n + 1) * 12 + (size_t)n + m + 256;
+}
+
+Engine::Engine(const HostConfig& cfg, int device) : impl_(new Impl), host_(cfg) {
+    impl_->device = device;
+    if (!flatten_config(cfg, dev_, lc_, err_)) return;
+#ifndef TSA_EMUL
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { err_ = "no CUDA device available: tsalign_b200 has no CPU path"; return; }
+    if (device < 0 || device >= count) { err_ = "invalid CUDA device index"; return; }
+    rt::check(cudaSetDevice(device), "cudaSetDevice");
+    rt::check(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : impl_->ev) rt::check(cudaEventCreate(&e), "cudaEventCreate");
+#endif
+    impl_->cfg.ensure(sizeof(DevConfig));
+    rt::h2d(impl_->cfg.p, &dev_, sizeof(DevConfig), impl_->stream);
+    impl_->lc.ensure(lc_.size() * sizeof(int));
+    rt::h2d(impl_->lc.p, lc_.data(), lc_.size() * sizeof(int), impl_->stream);
+    rt::stream_sync(impl_->stream);
+    ok_ = true;
+}
+
+Engine::~Engine() {
+#ifndef TSA_EMUL
+    if (ok_) {
+        cudaSetDevice(impl_->device);
+        for (auto& e : impl_->ev) cudaEventDestroy(e);
+        cudaStreamDestroy(impl_->stream);
+    }
+#endif
+    delete impl_;
+}
+
+bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
+    Impl& I = *impl_;
+#ifndef TSA_EMUL
+    rt::check(cudaSetDevice(I.device), "cudaSetDevice");
+#endif
+    I.opt = opt;
+    I.npairs = n;
+    I.ts_enabled = !opt.no_ts && dev_.n_kinds > 0;
+    I.metas.assign(n, PairMeta());
+    I.status.assign(n, PAIR_OK);
+    I.list_all.clear();
+    for (auto& l : I.class_list) l.clear();
+    for (auto& v : I.class_maxlen) v = 0;
+    size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0;
+    for (size_t i = 0; i < n; i++) {
+        const PairView& pv = pairs[i];
+        PairMeta& pm = I.metas[i];
+        pm.n = pv.n; pm.m = pv.m; pm.ro = pv.ro; pm.rl = pv.rl; pm.qo = pv.qo; pm.ql = pv.ql;
+        pm.seq_r = (long long)seq_bytes; seq_bytes += (size_t)pv.n;
+        pm.seq_q = (long long)seq_bytes; seq_bytes += (size_t)pv.m;
+        pm.vec = (long long)vec; vec += (size_t)pv.n + pv.m + 2;
+        pm.scr = (long long)scr; scr += 3 * ((size_t)pv.n + 1);
+        pm.mat = (long long)cells;
+        const int W = std::max(pv.n, pv.m) + 1;
+        if (I.ts_enabled) {
+            if (dev_.left_flank > 0 || dev_.right_flank > 0) { I.status[i] = PAIR_ERR_FLANKS; continue; }
+            int cls = -1;
+            for (int c = 0; c < N_CLASS; c++) if (W <= 32 * CLASS_C[c]) { cls = c; break; }
+            if (cls < 0) { I.status[i] = PAIR_ERR_TOO_LONG; continue; }
+            cells += (size_t)(pv.n + 1) * (pv.m + 1);
+            I.class_list[cls].push_back((int)i);
+            I.class_maxlen[cls] = std::max(I.class_maxlen[cls], W - 1);
+        }
+        I.list_all.push_back((int)i);
+    }
+    size_t need = seq_bytes + cells * 12 + vec * 4 + scr * 4 + n * (sizeof(PairMeta) + 32);
+    if (need > opt.chunk_bytes && n > 1) return false;
+    I.seqpool.resize(seq_bytes);
+    for (size_t i = 0; i < n; i++) {
+        if (pairs[i].n) memcpy(&I.seqpool[(size_t)I.metas[i].seq_r], pairs[i].ref, (size_t)pairs[i].n);
+        if (pairs[i].m) memcpy(&I.seqpool[(size_t)I.metas[i].seq_q], pairs[i].qry, (size_t)pairs[i].m);
+    }
+    I.meta.ensure(n * sizeof(PairMeta));
+    I.seq.ensure(seq_bytes);
+    I.minvec.ensure(vec * 4);
+    I.scratch.ensure(scr * 4);
+    I.best.ensure(n * 4); I.best_layer.ensure(n * 4); I.active.ensure(n * 4); I.next_active.ensure(n * 4);
+    I.counters.ensure(64);
+    if (I.ts_enabled) { I.D.ensure(cells * 2); I.DT.ensure(cells * 2); I.seedA.ensure(cells * 4); I.seedB.ensure(cells * 4); }
+    // pair lists: all, then one per class
+    std::vector<int> flat = I.list_all;
+    size_t off_class[N_CLASS];
+    for (int c = 0; c < N_CLASS; c++) { off_class[c] = flat.size(); flat.insert(flat.end(), I.class_list[c].begin(), I.class_list[c].end()); }
+    I.lists.ensure(std::max<size_t>(1, flat.size()) * 4);
+    rt::h2d(I.lists.p, flat.data(), flat.size() * 4, I.stream);
+    I.d_list_all = I.lists.as<int>();
+    for (int c = 0; c < N_CLASS; c++) I.d_class_list[c] = I.lists.as<int>() + off_class[c];
+    rt::h2d(I.meta.p, I.metas.data(), n * sizeof(PairMeta), I.stream);
+    rt::h2d(I.seq.p, I.seqpool.data(), seq_bytes, I.stream);
+    stats_.h2d_bytes = (long long)(n * sizeof(PairMeta) + seq_bytes + flat.size() * 4);
+
+    Chunk& ck = I.ck;
+    ck.pairs = I.meta.as<PairMeta>();
+    ck.seq = I.seq.as<uint8_t>();
+    ck.cfg = I.cfg.as<DevConfig>();
+    ck.lc = I.lc.as<int>();
+    ck.D = I.ts_enabled ? I.D.as<int16_t>() : nullptr;
+    ck.DT = I.ts_enabled ? I.DT.as<int16_t>() : nullptr;
+    ck.seedA = I.seedA.as<int>();
+    ck.seedB = I.seedB.as<int>();
+    ck.minvec = I.minvec.as<int>();
+    ck.scratch = I.scratch.as<int>();
+    ck.best = I.best.as<int>();
+    ck.best_layer = I.best_layer.as<int>();
+    ck.active = I.active.as<int>();
+    ck.next_active = I.next_active.as<int>();
+    ck.counters = I.counters.as<int>();
+    rt::stream_sync(I.stream);
+    return true;
+}
+
+void Engine::run_staged() {
+    Impl& I = *impl_;
+#ifndef TSA_EMUL
+    rt::check(cudaSetDevice(I.device), "cudaSetDevice");
+#endif
+    stats_.launches = stats_.fill_launches = stats_.jump_launches = 0;
+    stats_.layers_run = 0;
+    const int n_all = (int)I.list_all.size();
+    if (n_all == 0) return;
+    const size_t k1_smem = (size_t)K1_WARPS * MAX_ALPHABET * MAX_ALPHABET * sizeof(int);
+    const unsigned k1_grid = (unsigned)((n_all + K1_WARPS - 1) / K1_WARPS);
+    rt::dev_memset(I.active.p, 0, I.npairs * 4, I.stream);
+    rt::dev_memset(I.next_active.p, 0, I.npairs * 4, I.stream);
+    TSA_LAUNCH(k_primary_fill, dim3(k1_grid), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, I.d_list_all, n_all, 0);
+    stats_.launches++; stats_.fill_launches++;
+    if (!I.ts_enabled) return;
+
+    int n_ts = 0;
+    for (int c = 0; c < N_CLASS; c++) n_ts += (int)I.class_list[c].size();
+    if (n_ts == 0) return;
+    // the TS-enabled pairs are exactly the union of the class lists, which are contiguous after list_all
+    const int* d_ts_list = I.d_class_list[0];
+    const unsigned fill_grid = (unsigned)((n_ts + K1_WARPS - 1) / K1_WARPS);
+    for (int layer = 0; layer < I.opt.max_layers; layer++) {
+        rt::dev_memset(I.counters.p, 0, 64, I.stream);
+        for (int off = 0; off < n_ts; off += 65535) {
+            const int cnt = std::min(65535, n_ts - off);
+            TSA_LAUNCH(k_clear_seeds, dim3(8, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, d_ts_list + off, cnt);
+            stats_.launches++;
+        }
+        for (int c = 0; c < N_CLASS; c++) {
+            const int cnt = (int)I.class_list[c].size();
+            if (!cnt) continue;
+            long long l = 0;
+            switch (CLASS_C[c]) {
+            case 3: launch_jump<3>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+            case 5: launch_jump<5>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+            case 9: launch_jump<9>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+            case 17: launch_jump<17>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+            default: launch_jump<33>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+            }
+            stats_.launches += l; stats_.jump_launches += l;
+        }
+        TSA_LAUNCH(k_advance, dim3((unsigned)((n_ts + 255) / 256)), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts);
+        stats_.launches++;
+        int h_count = 0;
+        rt::d2h(&h_count, I.counters.p, 4, I.stream);
+        rt::stream_sync(I.stream);
+        stats_.layers_run = layer + 1;
+        if (h_count == 0) break;
+        TSA_LAUNCH(k_primary_fill, dim3(fill_grid), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_ts_list, n_ts, layer + 1);
+        stats_.launches++; stats_.fill_launches++;
+    }
+}
+
+void Engine::fetch_staged(PairCost* out) {
+    Impl& I = *impl_;
+    const size_t n = I.npairs;
+    I.h_best.resize(n); I.h_layer.resize(n); I.h_active.resize(n);
+    rt::d2h(I.h_best.data(), I.best.p, n * 4, I.stream);
+    rt::d2h(I.h_layer.data(), I.best_layer.p, n * 4, I.stream);
+    rt::d2h(I.h_active.data(), I.active.p, n * 4, I.stream);
+    rt::stream_sync(I.stream);
+    stats_.d2h_bytes = (long long)(n * 12);
+    for (size_t i = 0; i < n; i++) {
+        PairCost& pc = out[i];
+        pc = PairCost();
+        pc.status = I.status[i];
+        if (pc.status != PAIR_OK) continue;
+        if (I.h_best[i] >= INF32) { pc.status = PAIR_NO_TARGET; continue; }
+        // The jump kernel computes in saturating s16: every path cheaper than INF16 is exact, so a result below
+        // INF16 is the optimum; above it a cheaper template-switch path may have been saturated away.
+        if (I.ts_enabled && I.h_best[i] >= INF16 - 1) { pc.status = PAIR_ERR_COST_RANGE; continue; }
+        if (I.ts_enabled && I.h_active[i]) { pc.status = PAIR_ERR_LAYER_CAP; continue; }
+        pc.status = PAIR_OK;
+        pc.cost = I.h_best[i];
+        pc.layers = I.h_layer[i];
+    }
+}
+
+void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& opt, PairCost* out) {
+    // Greedy chunking in input order under the HBM budget.
+    size_t i = 0;
+    EngineStats total;
+    while (i < n) {
+        size_t j = i, bytes = 0;
+        while (j < n) {
+            const size_t b = (!opt.no_ts && dev_.n_kinds > 0) ? bytes_per_pair(pairs[j].n, pairs[j].m) : (size_t)(pairs[j].n + pairs[j].m) * 20 + 512;
+            if (j > i && bytes + b > opt.chunk_bytes) break;
+            bytes += b; j++;
+        }
+        AlignOptions o = opt;
+        o.chunk_bytes = std::max(opt.chunk_bytes, bytes * 2);
+        stage(pairs + i, j - i, o);
+        run_staged();
+        fetch_staged(out + i);
+        total.launches += stats_.launches; total.fill_launches += stats_.fill_launches; total.jump_launches += stats_.jump_launches;
+        total.layers_run = std::max(total.layers_run, stats_.layers_run);
+        total.h2d_bytes += stats_.h2d_bytes; total.d2h_bytes += stats_.d2h_bytes;
+        i = j;
+    }
+    stats_ = total;
+}
+
+}  // namespace tsa

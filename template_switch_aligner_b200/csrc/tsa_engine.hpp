@@ -1,0 +1,83 @@
+// tsa_engine.hpp -- host side of the hot path: batches of independent pairs -> chunks resident in HBM ->
+// layer loop (primary fill, TS jump) -> costs (and alignments).  One Engine per (config, device).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "tsa_config.hpp"
+#include "tsa_types.hpp"
+
+namespace tsa {
+
+struct AlignOptions {
+    bool no_ts = false;            // --no-ts: MaxTemplateSwitchCount(0), strategies/template_switch_count.rs:41-63
+    int max_layers = 64;           // cap on the number of template switches per alignment
+    size_t chunk_bytes = (size_t)6 << 30;  // HBM budget of one resident chunk of pairs
+};
+
+// One pair, already encoded as alphabet indices.
+struct PairView {
+    const uint8_t* ref; int n;
+    const uint8_t* qry; int m;
+    int ro, rl, qo, ql;            // AlignmentRange (offset / limit)
+};
+
+enum PairStatus {
+    PAIR_OK = 0,
+    PAIR_NO_TARGET = 1,            // AStarResult::NoTarget
+    PAIR_ERR_TOO_LONG = 2,         // TS-enabled pair longer than the jump kernel's widest instantiation
+    PAIR_ERR_COST_RANGE = 3,       // costs do not fit the packed s16 lanes of the jump kernel
+    PAIR_ERR_LAYER_CAP = 4,        // still improving after max_layers template switches
+    PAIR_ERR_FLANKS = 5,           // flank lengths > 0 with TS enabled: not built yet
+};
+
+struct PairCost {
+    int status = PAIR_OK;
+    int64_t cost = 0;              // optimal cost (status == PAIR_OK)
+    int layers = 0;                // number of template switches on the optimal path found (first layer reaching cost)
+};
+
+struct EngineStats {
+    long long launches = 0;        // kernels launched by the last run()
+    long long fill_launches = 0, jump_launches = 0;
+    int layers_run = 0;            // jump rounds of the last run (max over chunks)
+    double jump_ms = 0, fill_ms = 0;  // device time of the two kernel families (CUDA events; 0 in the emulator)
+    long long h2d_bytes = 0, d2h_bytes = 0;
+};
+
+class Engine {
+public:
+    Engine(const HostConfig& cfg, int device);
+    ~Engine();
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    bool ok() const { return ok_; }
+    const std::string& error() const { return err_; }
+    const DevConfig& dev_config() const { return dev_; }
+
+    // Whole job: chunk, upload, run, fetch.  out[i] matches pairs[i].
+    void align_costs(const PairView* pairs, size_t n, const AlignOptions& opt, PairCost* out);
+
+    // Split form used by the benchmark: make one chunk resident, run it any number of times, fetch.
+    // (All pairs must fit one chunk; returns false otherwise.)
+    bool stage(const PairView* pairs, size_t n, const AlignOptions& opt);
+    void run_staged();
+    void fetch_staged(PairCost* out);
+
+    const EngineStats& stats() const { return stats_; }
+    static size_t bytes_per_pair(int n, int m);
+
+private:
+    struct Impl;
+    Impl* impl_;
+    HostConfig host_;
+    DevConfig dev_;
+    std::vector<int> lc_;
+    bool ok_ = false;
+    std::string err_;
+    EngineStats stats_;
+};
+
+}  // namespace tsa
