@@ -115,7 +115,12 @@ tsa_batch* tsa_batch_create(const tsa_config* cfg, const tsa_options* opt, const
 int tsa_batch_run(tsa_batch* batch);                              /* kernels only; synchronous */
 int tsa_batch_fetch(tsa_batch* batch, tsa_result* out);           /* D2H + result assembly */
 void tsa_batch_stats(const tsa_batch* batch, int64_t* launches, int64_t* jump_launches, int64_t* fill_launches, int32_t* layers, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* device time (CUDA events on the engine's stream) of the two kernel families during the last tsa_batch_run */
+void tsa_batch_timing(const tsa_batch* batch, double* jump_ms, double* fill_ms);
 void tsa_batch_free(tsa_batch* batch);
+
+/* Integer roofline probe: measured issue rate (lanes/s) of the DPX add-min instructions on all SMs. */
+int tsa_measure_addmin_peak(int device, double* s16x2_lane_ops_per_s, double* s32_lane_ops_per_s);
 
 /* ---- misc ----------------------------------------------------------------------------------------------- */
 int tsa_device_count(void);

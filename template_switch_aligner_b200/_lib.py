@@ -28,7 +28,7 @@ OP_NAMES = [
 EXPORTS = [
     "tsa_config_parse", "tsa_config_default", "tsa_config_write", "tsa_config_free", "tsa_config_alphabet",
     "tsa_align_batch", "tsa_results_free", "tsa_batch_create", "tsa_batch_run", "tsa_batch_fetch", "tsa_batch_stats",
-    "tsa_batch_free", "tsa_device_count", "tsa_version",
+    "tsa_batch_free", "tsa_batch_timing", "tsa_measure_addmin_peak", "tsa_device_count", "tsa_version",
 ]
 
 
@@ -83,6 +83,10 @@ def bind(cdll):
     cdll.tsa_batch_fetch.argtypes = [C.c_void_p, C.POINTER(TsaResult)]
     cdll.tsa_batch_stats.restype = None
     cdll.tsa_batch_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3 + [C.POINTER(C.c_int32)] + [C.POINTER(C.c_int64)] * 2
+    cdll.tsa_batch_timing.restype = None
+    cdll.tsa_batch_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    cdll.tsa_measure_addmin_peak.restype = C.c_int
+    cdll.tsa_measure_addmin_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     cdll.tsa_batch_free.restype = None
     cdll.tsa_batch_free.argtypes = [C.c_void_p]
     cdll.tsa_device_count.restype = C.c_int

@@ -309,6 +309,12 @@ class StagedBatch:
         self._lib.tsa_batch_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e), C.byref(f))
         return {"launches": a.value, "jump_launches": b.value, "fill_launches": c.value, "layers": d.value, "h2d_bytes": e.value, "d2h_bytes": f.value}
 
+    def timing(self) -> dict:
+        """Device time of the last run() per kernel family (CUDA events on the engine's stream)."""
+        j, f = C.c_double(), C.c_double()
+        self._lib.tsa_batch_timing(self._h, C.byref(j), C.byref(f))
+        return {"jump_ms": j.value, "fill_ms": f.value}
+
     def close(self):
         h, self._h = getattr(self, "_h", None), None
         if h:

@@ -203,6 +203,21 @@ void tsa_batch_stats(const tsa_batch* b, int64_t* launches, int64_t* jump_launch
     if (d2h_bytes) *d2h_bytes = s.d2h_bytes;
 }
 
+void tsa_batch_timing(const tsa_batch* b, double* jump_ms, double* fill_ms) {
+    if (!b) return;
+    if (jump_ms) *jump_ms = b->engine->stats().jump_ms;
+    if (fill_ms) *fill_ms = b->engine->stats().fill_ms;
+}
+
+int tsa_measure_addmin_peak(int device, double* s16x2_lane_ops_per_s, double* s32_lane_ops_per_s) {
+    std::string err;
+    double a = 0, c = 0;
+    if (!measure_addmin_peak(device, &a, &c, err)) return TSA_ERR_NO_DEVICE;
+    if (s16x2_lane_ops_per_s) *s16x2_lane_ops_per_s = a;
+    if (s32_lane_ops_per_s) *s32_lane_ops_per_s = c;
+    return TSA_OK;
+}
+
 void tsa_batch_free(tsa_batch* b) { delete b; }
 
 int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pairs, size_t n, tsa_result* out, char* err, size_t errcap) {

@@ -215,13 +215,24 @@ void Engine::run_staged() {
     const unsigned k1_grid = (unsigned)((n_all + K1_WARPS - 1) / K1_WARPS);
     rt::dev_memset(I.active.p, 0, I.npairs * 4, I.stream);
     rt::dev_memset(I.next_active.p, 0, I.npairs * 4, I.stream);
+    stats_.jump_ms = stats_.fill_ms = 0;
+#ifndef TSA_EMUL
+    auto mark = [&](int k) { rt::check(cudaEventRecord(I.ev[k], I.stream), "cudaEventRecord"); };
+    auto span = [&](int a, int b) { float ms = 0; rt::check(cudaEventSynchronize(I.ev[b]), "cudaEventSynchronize"); cudaEventElapsedTime(&ms, I.ev[a], I.ev[b]); return (double)ms; };
+#else
+    auto mark = [&](int) {};
+    auto span = [&](int, int) { return 0.0; };
+#endif
+    mark(0);
     TSA_LAUNCH(k_primary_fill, dim3(k1_grid), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, I.d_list_all, n_all, 0);
+    mark(1);
     stats_.launches++; stats_.fill_launches++;
-    if (!I.ts_enabled) return;
+    if (!I.ts_enabled) { rt::stream_sync(I.stream); stats_.fill_ms += span(0, 1); return; }
 
     int n_ts = 0;
     for (int c = 0; c < N_CLASS; c++) n_ts += (int)I.class_list[c].size();
-    if (n_ts == 0) return;
+    if (n_ts == 0) { rt::stream_sync(I.stream); stats_.fill_ms += span(0, 1); return; }
+    bool fill_pending = true;   // events 0..1 bracket a fill that has not been read yet
     // the TS-enabled pairs are exactly the union of the class lists, which are contiguous after list_all
     const int* d_ts_list = I.d_class_list[0];
     const unsigned fill_grid = (unsigned)((n_ts + K1_WARPS - 1) / K1_WARPS);
@@ -232,6 +243,7 @@ void Engine::run_staged() {
             TSA_LAUNCH(k_clear_seeds, dim3(8, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, d_ts_list + off, cnt);
             stats_.launches++;
         }
+        mark(2);
         for (int c = 0; c < N_CLASS; c++) {
             const int cnt = (int)I.class_list[c].size();
             if (!cnt) continue;
@@ -245,14 +257,21 @@ void Engine::run_staged() {
             }
             stats_.launches += l; stats_.jump_launches += l;
         }
+        mark(3);
         TSA_LAUNCH(k_advance, dim3((unsigned)((n_ts + 255) / 256)), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts);
         stats_.launches++;
         int h_count = 0;
         rt::d2h(&h_count, I.counters.p, 4, I.stream);
         rt::stream_sync(I.stream);
+        if (fill_pending) { stats_.fill_ms += span(0, 1); fill_pending = false; }
+        stats_.jump_ms += span(2, 3);
         stats_.layers_run = layer + 1;
         if (h_count == 0) break;
+        if (layer + 1 >= I.opt.max_layers) break;
+        mark(0);
         TSA_LAUNCH(k_primary_fill, dim3(fill_grid), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_ts_list, n_ts, layer + 1);
+        mark(1);
+        fill_pending = true;
         stats_.launches++; stats_.fill_launches++;
     }
 }
@@ -304,6 +323,64 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
         i = j;
     }
     stats_ = total;
+}
+
+// ---- integer roofline probe: back-to-back DPX add-min on every SM ---------------------------------------------
+// 8 independent dependency chains per thread so that the issue rate, not the latency, is measured.
+TSA_KERNEL void k_addmin_probe(uint32_t* out, int iters, int packed) {
+    uint32_t a[8];
+    const uint32_t t = (uint32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = (t * 2654435761u + (uint32_t)k * 40503u) & 0x0fff0fffu;
+    const uint32_t b = (t & 7u) | ((t & 3u) << 16), c = 0x3fff3fffu;
+    if (packed) {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[k] = addmin_s16x2(a[k], b, c ^ a[(k + 1) & 7]);
+        }
+    } else {
+        for (int i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[k] = (uint32_t)addmin_s32((int)a[k], (int)b, (int)(c ^ a[(k + 1) & 7]));
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r ^= a[k];
+    if (r == 0x12345678u) out[t & 1023] = r;  // keeps the chains alive
+}
+
+bool measure_addmin_peak(int device, double* s16x2_lane_ops_per_s, double* s32_lane_ops_per_s, std::string& err) {
+#ifndef TSA_EMUL
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { err = "no CUDA device"; return false; }
+    rt::check(cudaSetDevice(device), "cudaSetDevice");
+    cudaDeviceProp prop;
+    rt::check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+    uint32_t* d = (uint32_t*)rt::dev_alloc(4096);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 4096, threads = 256, blocks = prop.multiProcessorCount * 8;
+    // the xor feeding operand c is one extra ALU op per add-min: count only the add-min lanes (a lower bound on peak)
+    for (int packed = 1; packed >= 0; packed--) {
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0);
+            k_addmin_probe<<<blocks, threads>>>(d, iters, packed);
+            cudaEventRecord(e1);
+            rt::check(cudaEventSynchronize(e1), "probe");
+            float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+            const double ops = (double)blocks * threads * iters * 8 * (packed ? 2 : 1);
+            if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+        }
+        *(packed ? s16x2_lane_ops_per_s : s32_lane_ops_per_s) = best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    rt::dev_free(d);
+    return true;
+#else
+    (void)device; *s16x2_lane_ops_per_s = 0; *s32_lane_ops_per_s = 0; err = "emulator"; return false;
+#endif
 }
 
 }  // namespace tsa

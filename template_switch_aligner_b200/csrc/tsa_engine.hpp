@@ -80,4 +80,7 @@ private:
     EngineStats stats_;
 };
 
+// Measured issue rate of the DPX add-min instructions (lanes per second), the denominator of the integer roofline.
+bool measure_addmin_peak(int device, double* s16x2_lane_ops_per_s, double* s32_lane_ops_per_s, std::string& err);
+
 }  // namespace tsa

@@ -79,3 +79,27 @@ def parse_config_any(text):
         except tsa_config.ConfigError:
             pass
     raise tsa_config.ConfigError("no alphabet fits")
+
+
+def config_to_text(cfg):
+    """oracle tsa_config.Config -> config.tsa text (the syntax of sample_tsa_config/config.tsa)."""
+    def cost(v):
+        return "inf" if v == tsa_config.INF else str(v)
+
+    def idx(v):
+        return "-inf" if v == tsa_config.I64_MIN else ("inf" if v == tsa_config.I64_MAX else str(v))
+
+    out = ["# Limits", "", f"left_flank_length = {cfg.left_flank_length}", f"right_flank_length = {cfg.right_flank_length}", "", "# Base Cost", ""]
+    for name, v in zip(tsa_config.BASE_NAMES, cfg.base):
+        out.append(f"{name}_cost = {cost(v)}")
+    out += ["", "# Jump Costs", ""]
+    for name, pts in zip(tsa_config.FN_NAMES, cfg.fns):
+        out += [name, " " + " ".join(idx(x) for x, _ in pts), " " + " ".join(cost(c) for _, c in pts), ""]
+    chars = cfg.chars
+    for t in cfg.tables:
+        out += [f"# {t.name}", "", "SubstitutionCostTable", "  | " + " ".join(chars), "--+" + "-" * (2 * len(chars))]
+        for r, ch in enumerate(chars):
+            out.append(f"{ch} | " + " ".join(cost(v) for v in t.sub[r]))
+        out += ["", "GapOpenCostVector", " " + " ".join(chars), " " + " ".join(cost(v) for v in t.open), "",
+                "GapExtendCostVector", " " + " ".join(chars), " " + " ".join(cost(v) for v in t.ext), ""]
+    return "\n".join(out) + "\n"

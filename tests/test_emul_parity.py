@@ -1,0 +1,60 @@
+"""Kernel logic on the CPU: the product sources compiled against the SIMT emulator (tests/emul) must agree with the
+oracle.  These tests exercise exactly the code the GPU runs (same .cuh), minus the hardware."""
+import pytest
+
+from oracle import oracle
+from helpers import parse_config_any
+from emul_lib import emul
+import parity
+import template_switch_aligner_b200 as tsa
+
+
+def test_random_models_emulated():
+    n_ts = parity.random_model_batches(emul(), range(0, 60), max_len=14)
+    assert n_ts > 10
+
+
+@pytest.mark.parametrize("cfg_name,max_len", [("sample", 45), ("bench", 40), ("small", 40)])
+def test_test_files_emulated(configs, pairs, cfg_name, max_len):
+    ocfg = parse_config_any(configs[cfg_name])
+    flat = oracle.FlatConfig(ocfg)
+    items = parity.test_file_pairs(pairs, ocfg.alphabet, max_len)
+    assert len(items) >= 15
+    for no_ts in (False, True):
+        aligner = tsa.Aligner(costs=configs[cfg_name], alphabet=ocfg.alphabet, no_ts=no_ts, lib=emul())
+        parity.check_batch(aligner, flat, [(r, q) for _, r, q in items], no_ts=no_ts, label=cfg_name)
+
+
+def test_tsnax_kat_emulated(configs, kats):
+    # lib_tsalign/src/tests.rs:38-194 through the emulated kernels: 416 x 416 bp (jump kernel class C = 17)
+    k = kats["tsnax_disc1_473"]
+    aligner = tsa.Aligner(costs=configs[k["config"]], alphabet=k["alphabet"], lib=emul())
+    res = aligner.align_batch([(k["reference"], k["query"], tuple(k["range"]))])[0]
+    assert res.found and res.cost == k["cost"]
+
+
+def test_edge_cases_emulated(configs):
+    ocfg = parse_config_any(configs["sample"])
+    flat = oracle.FlatConfig(ocfg)
+    aligner = tsa.Aligner(costs=configs["sample"], lib=emul())
+    cases = [("", ""), ("A", ""), ("", "ACGT"), ("ACGTN", "NNNNN"), ("ACGT" * 8, "ACGT" * 8, (3, 3, 5, 5)), ("ACGTACGTAC", "ACGTTCGTAC", (0, 10, 0, 10))]
+    parity.check_batch(aligner, flat, cases, label="edge")
+    # invalid characters / ranges are per-pair input errors (align.rs:389-405), the rest of the batch still runs
+    res = aligner.align_batch([("ACGX", "ACGT"), ("ACGT", "ACGT", (3, 2, 0, 4)), ("ACGT", "ACGT")])
+    assert [r.status for r in res] == [7, 8, 0] and res[2].cost == 0
+    # cost limit semantics of the exact fill
+    res = aligner.align_batch([("ACGTACGTAC", "ACGTTCGTAC")], cost_limit=1)[0]
+    assert res.result_type == "ExceededCostLimit" and res.cost == 1
+    res = aligner.align_batch([("ACGTACGTAC", "ACGTTCGTAC")], cost_limit=2)[0]
+    assert res.found and res.cost == 2
+
+
+def test_python_surface_emulated(configs):
+    # mirror of python_bindings/python/tsalign/__init__.py: align() returns None when no target within limits
+    a = tsa.align("ACGTACGTAC", "ACGTTCGTAC", costs=configs["sample"], lib=emul())
+    assert a is not None and a.cost == 2 and a.stats()["result"]["astar_result_type"] == "FoundTarget"
+    assert tsa.align("ACGTACGTAC", "ACGTTCGTAC", costs=configs["sample"], cost_limit=0, lib=emul()) is None
+    with pytest.raises(ValueError):
+        tsa.Aligner(costs="x", costs_file="y", lib=emul())
+    with pytest.raises(ValueError):
+        tsa.Aligner(min_length_strategy="bogus", lib=emul())

@@ -1,0 +1,138 @@
+"""Parity of the CUDA path (through the C ABI of libtsalign_b200.so) against the CPU oracle.  Needs a B200."""
+import pytest
+
+from oracle import oracle, tsa_config
+from helpers import parse_config_any
+import parity
+import template_switch_aligner_b200 as tsa
+from template_switch_aligner_b200 import _lib, workloads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    lib = _lib.default()
+    assert lib.tsa_device_count() >= 1, "no CUDA device: the GPU tests cannot run"
+    assert b"sm_100a" in lib.tsa_version()
+    return lib
+
+
+def test_random_models_gpu(lib):
+    n_ts = parity.random_model_batches(lib, range(0, 150), max_len=20, pairs_per_model=8)
+    assert n_ts > 30
+
+
+@pytest.mark.parametrize("cfg_name,max_len", [("sample", 130), ("bench", 130), ("experiments", 110), ("small", 130), ("no_intra_forward_jump", 130)])
+def test_test_files_gpu(lib, configs, pairs, cfg_name, max_len):
+    ocfg = parse_config_any(configs[cfg_name])
+    flat = oracle.FlatConfig(ocfg)
+    items = parity.test_file_pairs(pairs, ocfg.alphabet, max_len)
+    assert len(items) >= 30
+    for no_ts in (False, True):
+        aligner = tsa.Aligner(costs=configs[cfg_name], alphabet=ocfg.alphabet, no_ts=no_ts, lib=lib)
+        parity.check_batch(aligner, flat, [(r, q) for _, r, q in items], no_ts=no_ts, label=cfg_name)
+
+
+def test_test_files_long_gpu(lib, configs, pairs):
+    # 200 .. 1127 bp pairs of test_files (jump kernel classes C = 9, 17, 33), sample config
+    ocfg = parse_config_any(configs["sample"])
+    flat = oracle.FlatConfig(ocfg)
+    items = parity.test_file_pairs(pairs, ocfg.alphabet, 1055, min_len=131)
+    assert len(items) >= 15
+    aligner = tsa.Aligner(costs=configs["sample"], alphabet=ocfg.alphabet, lib=lib)
+    parity.check_batch(aligner, flat, [(r, q) for _, r, q in items], label="long")
+
+
+def test_reference_kats_gpu(lib, configs, kats):
+    k = kats["tsnax_disc1_473"]  # lib_tsalign/src/tests.rs:38-194
+    aligner = tsa.Aligner(costs=configs[k["config"]], alphabet=k["alphabet"], lib=lib)
+    res = aligner.align_batch([(k["reference"], k["query"], tuple(k["range"]))])[0]
+    assert res.found and res.cost == k["cost"]
+    k = kats["match_overtakes_gap"]  # lib_tsalign/src/a_star_aligner/tests.rs:10-29
+    cfg = tsa_config.rust_default(k["alphabet"])
+    cfg.tables[0] = tsa_config.base_agnostic(k["alphabet"], "Primary Edit Costs", k["match"], k["substitution"], k["gap_open"], k["gap_extend"])
+    from helpers import config_to_text
+    aligner = tsa.Aligner(costs=config_to_text(cfg), alphabet=k["alphabet"], no_ts=True, lib=lib)
+    res = aligner.align_batch([(k["reference"], k["query"])])[0]
+    assert res.found and res.cost == k["cost"]
+
+
+def test_golden_toml_costs_gpu(lib, configs, toml_golden):
+    # the committed result files: same sequences + recorded range -> at most the recorded cost, and equal to the oracle
+    for name, g in toml_golden.items():
+        p = g["parsed"]
+        if p["type"] != "WithTarget" or "no_ts" in name:
+            continue
+        seqs = p["sequences"]
+        ocfg = parse_config_any(configs[g["config"]])
+        try:
+            oracle.alphabets.encode(ocfg.alphabet, seqs["reference"]), oracle.alphabets.encode(ocfg.alphabet, seqs["query"])
+        except ValueError:
+            ocfg = tsa_config.parse(configs[g["config"]], "dna-n") if ocfg.alphabet == "dna-n" else ocfg
+        aligner = tsa.Aligner(costs=configs[g["config"]], alphabet=ocfg.alphabet, lib=lib)
+        res = aligner.align_batch([(seqs["reference"], seqs["query"])])[0]
+        if res.status != 0:
+            continue  # longer than the widest jump kernel
+        assert res.found and res.cost <= int(p["cost"]), (name, res.cost, p["cost"])
+
+
+def test_read_pair_batch_gpu(lib):
+    # C2-shaped workload: 150 bp read pairs with a planted template switch, default `tsalign align` cost model
+    text = workloads.sample_config_text()
+    flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+    pairs = workloads.read_pairs(96)
+    aligner = tsa.Aligner(costs=text, lib=lib)
+    n_ts = parity.check_batch(aligner, flat, pairs, label="reads")
+    assert n_ts >= 48  # the planted TSMs are found
+
+
+def test_full_size_properties_gpu(lib):
+    # BASELINE config 2 at batch scale (no oracle): size-independent properties of the optimum
+    text = workloads.sample_config_text()
+    aligner = tsa.Aligner(costs=text, lib=lib)
+    no_ts = tsa.Aligner(costs=text, no_ts=True, lib=lib)
+    pairs = workloads.read_pairs(4096, start=10_000)
+    a = aligner.align_batch(pairs)
+    b = no_ts.align_batch(pairs)
+    again = aligner.align_batch(list(reversed(pairs)))
+    for x, y, z, (r, q) in zip(a, b, reversed(again), pairs):
+        assert x.found and y.found
+        assert x.cost <= y.cost                       # template switches can only help
+        assert x.cost == z.cost                       # independent of batch position
+        assert (x.cost == 0) == (r == q)              # zero cost iff identical (sample model: every edit costs)
+    # identical pairs cost 0; a pair against itself reversed-complemented once is one template switch
+    same = aligner.align_batch([(r, r) for r, _ in pairs[:64]])
+    assert all(s.found and s.cost == 0 for s in same)
+    # swapping reference and query keeps the optimum (the sample cost model is symmetric in R/Q)
+    sw = aligner.align_batch([(q, r) for r, q in pairs[:256]])
+    assert [s.cost for s in sw] == [x.cost for x in a[:256]]
+
+
+def test_edge_cases_gpu(lib, configs):
+    ocfg = parse_config_any(configs["sample"])
+    flat = oracle.FlatConfig(ocfg)
+    aligner = tsa.Aligner(costs=configs["sample"], lib=lib)
+    cases = [("", ""), ("A", ""), ("", "ACGT"), ("ACGTN", "NNNNN"), ("ACGT" * 8, "ACGT" * 8, (3, 3, 5, 5)), ("ACGTACGTAC", "ACGTTCGTAC", (0, 10, 0, 10))]
+    parity.check_batch(aligner, flat, cases, label="edge")
+    res = aligner.align_batch([("ACGX", "ACGT"), ("ACGT", "ACGT", (3, 2, 0, 4)), ("ACGT", "ACGT")])
+    assert [r.status for r in res] == [7, 8, 0] and res[2].cost == 0
+    assert aligner.align_batch([]) == []
+    # a 3 kb pair with template switches enabled is refused loudly in this build, and runs with --no-ts
+    r, q = workloads.long_pair(0, 3000)
+    res = aligner.align_batch([(r, q)])[0]
+    assert res.status == 9
+    nots = tsa.Aligner(costs=configs["sample"], no_ts=True, lib=lib)
+    want = oracle.dp_align(flat, r, q, no_ts=True)
+    assert nots.align_batch([(r, q)])[0].cost == want.cost
+
+
+def test_no_ts_long_gpu(lib):
+    # BASELINE config 4 shape (10 kb, --no-ts) at 2 pairs: column-tiled primary fill
+    text = workloads.sample_config_text()
+    flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+    nots = tsa.Aligner(costs=text, no_ts=True, lib=lib)
+    pairs = [workloads.long_pair(i, 4000) for i in range(2)]
+    res = nots.align_batch(pairs)
+    for (r, q), g in zip(pairs, res):
+        assert g.found and g.cost == oracle.dp_align(flat, r, q, no_ts=True).cost
