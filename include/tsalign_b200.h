@@ -62,7 +62,7 @@ typedef struct {
     uint64_t cost_limit;           /* --cost-limit, UINT64_MAX = none: optimal cost > limit -> ExceededCostLimit */
     uint64_t memory_limit;         /* --memory-limit in bytes, UINT64_MAX = none: bounds the resident HBM chunk */
     int32_t max_template_switches; /* 0 = default (64) */
-    int32_t reserved;
+    int32_t first_threshold;       /* 0 = default (12): first pruning threshold of the iterative deepening; tuning only, never changes results */
 } tsa_options;
 
 /* ---- one alignment problem: the arguments of Aligner::align (configurable_a_star_align.rs:214-236) ------ */
@@ -117,6 +117,8 @@ int tsa_batch_fetch(tsa_batch* batch, tsa_result* out);           /* D2H + resul
 void tsa_batch_stats(const tsa_batch* batch, int64_t* launches, int64_t* jump_launches, int64_t* fill_launches, int32_t* layers, int64_t* h2d_bytes, int64_t* d2h_bytes);
 /* device time (CUDA events on the engine's stream) of the two kernel families during the last tsa_batch_run */
 void tsa_batch_timing(const tsa_batch* batch, double* jump_ms, double* fill_ms);
+/* work done by the jump kernel during the last tsa_batch_run: chain pairs started / not pruned, rows filled, rows jumped */
+void tsa_batch_work(const tsa_batch* batch, int64_t* chains_started, int64_t* chains_run, int64_t* rows_filled, int64_t* rows_jumped);
 void tsa_batch_free(tsa_batch* batch);
 
 /* Integer roofline probe: measured issue rate (lanes/s) of the DPX add-min instructions on all SMs. */

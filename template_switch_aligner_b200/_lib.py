@@ -28,13 +28,13 @@ OP_NAMES = [
 EXPORTS = [
     "tsa_config_parse", "tsa_config_default", "tsa_config_write", "tsa_config_free", "tsa_config_alphabet",
     "tsa_align_batch", "tsa_results_free", "tsa_batch_create", "tsa_batch_run", "tsa_batch_fetch", "tsa_batch_stats",
-    "tsa_batch_free", "tsa_batch_timing", "tsa_measure_addmin_peak", "tsa_device_count", "tsa_version",
+    "tsa_batch_free", "tsa_batch_timing", "tsa_batch_work", "tsa_measure_addmin_peak", "tsa_device_count", "tsa_version",
 ]
 
 
 class TsaOptions(C.Structure):
     _fields_ = [("no_ts", C.c_int32), ("device", C.c_int32), ("cost_limit", C.c_uint64), ("memory_limit", C.c_uint64),
-                ("max_template_switches", C.c_int32), ("reserved", C.c_int32)]
+                ("max_template_switches", C.c_int32), ("first_threshold", C.c_int32)]
 
 
 class TsaPair(C.Structure):
@@ -85,6 +85,8 @@ def bind(cdll):
     cdll.tsa_batch_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 3 + [C.POINTER(C.c_int32)] + [C.POINTER(C.c_int64)] * 2
     cdll.tsa_batch_timing.restype = None
     cdll.tsa_batch_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    cdll.tsa_batch_work.restype = None
+    cdll.tsa_batch_work.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 4
     cdll.tsa_measure_addmin_peak.restype = C.c_int
     cdll.tsa_measure_addmin_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     cdll.tsa_batch_free.restype = None

@@ -105,13 +105,14 @@ def _make_pairs(pairs: Sequence[tuple]):
     return arr, keep
 
 
-def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0) -> TsaOptions:
+def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0) -> TsaOptions:
     o = TsaOptions()
     o.no_ts = int(bool(no_ts))
     o.device = device
     o.cost_limit = U64_MAX if cost_limit is None else int(cost_limit)
     o.memory_limit = U64_MAX if memory_limit is None else int(memory_limit)
     o.max_template_switches = max_template_switches
+    o.first_threshold = first_threshold
     return o
 
 
@@ -221,7 +222,8 @@ class Aligner:
 
     def __init__(self, *, no_ts: bool = False, min_length_strategy: str = "lookahead", chaining_strategy: str = "none",
                  total_length_strategy: str = "maximise", costs: Optional[str] = None,
-                 costs_file: Optional[Union[str, pathlib.Path]] = None, alphabet: str = "dna-n", device: int = 0, lib=None) -> None:
+                 costs_file: Optional[Union[str, pathlib.Path]] = None, alphabet: str = "dna-n", device: int = 0,
+                 first_threshold: int = 0, lib=None) -> None:
         if costs is not None and costs_file is not None:
             raise ValueError("Provide at most one of 'costs' or 'costs_file'.")
         if min_length_strategy not in _MIN_LENGTH:
@@ -235,6 +237,7 @@ class Aligner:
         self._lib = lib or _lib.default()
         self.no_ts = bool(no_ts)
         self.device = device
+        self.first_threshold = first_threshold  # tuning of the exact pruning only; results do not depend on it
         self.config = Config(costs, alphabet, lib=self._lib)
 
     # -- batch entry point: the call the GPU path is built for ----------------------------------------------
@@ -243,7 +246,7 @@ class Aligner:
         arr, keep = _make_pairs(pairs)
         res = (TsaResult * max(1, len(pairs)))()
         err = C.create_string_buffer(512)
-        opt = _options(self.no_ts, self.device, cost_limit, memory_limit)
+        opt = _options(self.no_ts, self.device, cost_limit, memory_limit, first_threshold=self.first_threshold)
         rc = self._lib.tsa_align_batch(self.config._h, C.byref(opt), arr, len(pairs), res, err, len(err))
         if rc != 0:
             raise TsaError(rc, err.value.decode(errors="replace"))
@@ -271,7 +274,7 @@ class Aligner:
 
 def align(reference: object, query: object, **kwargs: object) -> Optional[Alignment]:
     """One-call convenience wrapper (mirror of tsalign.align)."""
-    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib")}
+    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib", "first_threshold")}
     align_kwargs = {k: v for k, v in kwargs.items() if k not in aligner_kwargs}
     return Aligner(**aligner_kwargs).align(reference, query, **align_kwargs)
 
@@ -286,7 +289,7 @@ class StagedBatch:
         arr, keep = _make_pairs(pairs)
         status = C.c_int(0)
         err = C.create_string_buffer(512)
-        opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit)
+        opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit, first_threshold=aligner.first_threshold)
         self._h = self._lib.tsa_batch_create(aligner.config._h, C.byref(opt), arr, self.n, C.byref(status), err, len(err))
         if not self._h:
             raise TsaError(status.value, err.value.decode(errors="replace"))
@@ -313,7 +316,10 @@ class StagedBatch:
         """Device time of the last run() per kernel family (CUDA events on the engine's stream)."""
         j, f = C.c_double(), C.c_double()
         self._lib.tsa_batch_timing(self._h, C.byref(j), C.byref(f))
-        return {"jump_ms": j.value, "fill_ms": f.value}
+        w = [C.c_int64() for _ in range(4)]
+        self._lib.tsa_batch_work(self._h, *[C.byref(x) for x in w])
+        return {"jump_ms": j.value, "fill_ms": f.value, "chains_started": w[0].value, "chains_run": w[1].value,
+                "rows_filled": w[2].value, "rows_jumped": w[3].value}
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None

@@ -99,6 +99,7 @@ AlignOptions engine_options(const tsa_options& o) {
     AlignOptions a;
     a.no_ts = o.no_ts != 0;
     if (o.max_template_switches > 0) a.max_layers = o.max_template_switches;
+    if (o.first_threshold > 0) a.first_threshold = o.first_threshold;
     if (o.memory_limit != UINT64_MAX) a.chunk_bytes = (size_t)std::max<uint64_t>(o.memory_limit, (uint64_t)1 << 20);
     return a;
 }
@@ -201,6 +202,15 @@ void tsa_batch_stats(const tsa_batch* b, int64_t* launches, int64_t* jump_launch
     if (layers) *layers = s.layers_run;
     if (h2d_bytes) *h2d_bytes = s.h2d_bytes;
     if (d2h_bytes) *d2h_bytes = s.d2h_bytes;
+}
+
+void tsa_batch_work(const tsa_batch* b, int64_t* chains_started, int64_t* chains_run, int64_t* rows_filled, int64_t* rows_jumped) {
+    if (!b) return;
+    const EngineStats& s = b->engine->stats();
+    if (chains_started) *chains_started = s.chains_started;
+    if (chains_run) *chains_run = s.chains_run;
+    if (rows_filled) *rows_filled = s.rows_filled;
+    if (rows_jumped) *rows_jumped = s.rows_jumped;
 }
 
 void tsa_batch_timing(const tsa_batch* b, double* jump_ms, double* fill_ms) {

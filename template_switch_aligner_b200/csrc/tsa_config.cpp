@@ -424,9 +424,23 @@ bool flatten_config(const HostConfig& cfg, DevConfig& dev, std::vector<int>& lc_
                 }
             }
         }
+        {   // merge adjacent pieces of equal cost (fewer window queries per row)
+            std::sort(oc.begin(), oc.end(), [](const Piece& a, const Piece& b) { return a.lo < b.lo; });
+            std::vector<Piece> merged;
+            for (const Piece& pc : oc) {
+                if (!merged.empty() && merged.back().cost == pc.cost && merged.back().hi + 1 == pc.lo) merged.back().hi = pc.hi;
+                else merged.push_back(pc);
+            }
+            oc.swap(merged);
+        }
         if (oc.size() > (size_t)MAX_PIECES) { err = "offset cost function has too many pieces (unsupported)"; return false; }
         if (oc.empty() || apg[d].empty() || ld.empty()) continue;
         kd.n_oc = (int)oc.size();
+        kd.oc_lo = oc.front().lo; kd.oc_hi = oc.back().hi;
+        kd.min_open = INF32;
+        for (int x = 0; x < A; x++) kd.min_open = std::min(kd.min_open, dev.open[kd.table][x]);
+        kd.oc_skip0 = 1;
+        for (const Piece& pc : oc) if (pc.lo <= 0 && 0 <= pc.hi) kd.oc_skip0 = 0;
         for (size_t i = 0; i < oc.size(); i++) kd.oc[i] = oc[i];
         kd.n_apg = (int)apg[d].size();
         for (size_t i = 0; i < apg[d].size(); i++) kd.apg[i] = apg[d][i];

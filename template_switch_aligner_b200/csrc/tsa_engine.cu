@@ -67,7 +67,7 @@ void launch_jump(const Chunk& ck, const int* d_list, int n_list, int max_len, in
 struct Engine::Impl {
     int device = 0;
     cudaStream_t stream = 0;
-    DevBuf cfg, lc, meta, seq, D, DT, seedA, seedB, minvec, scratch, best, best_layer, active, next_active, counters, lists;
+    DevBuf cfg, lc, meta, seq, D, DT, seedA, seedB, minvec, scratch, best, best_layer, active, next_active, counters, lists, thr, ub, t0, resolved;
     std::vector<PairMeta> metas;
     std::vector<uint8_t> seqpool;
     std::vector<int> status;            // per staged pair (PairStatus)
@@ -78,7 +78,7 @@ struct Engine::Impl {
     int* d_class_list[N_CLASS] = {nullptr};
     size_t npairs = 0;
     AlignOptions opt;
-    Chunk ck;
+    Chunk ck = Chunk();
     bool ts_enabled = false;
     std::vector<int> h_best, h_layer, h_active;
 #ifndef TSA_EMUL
@@ -169,6 +169,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.scratch.ensure(scr * 4);
     I.best.ensure(n * 4); I.best_layer.ensure(n * 4); I.active.ensure(n * 4); I.next_active.ensure(n * 4);
     I.counters.ensure(64);
+    I.thr.ensure(n * 4); I.ub.ensure(n * 4); I.t0.ensure(n * 4); I.resolved.ensure(n * 4);
     if (I.ts_enabled) { I.D.ensure(cells * 2); I.DT.ensure(cells * 2); I.seedA.ensure(cells * 4); I.seedB.ensure(cells * 4); }
     // pair lists: all, then one per class
     std::vector<int> flat = I.list_all;
@@ -189,6 +190,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.lc = I.lc.as<int>();
     ck.D = I.ts_enabled ? I.D.as<int16_t>() : nullptr;
     ck.DT = I.ts_enabled ? I.DT.as<int16_t>() : nullptr;
+    ck.dir = nullptr;
     ck.seedA = I.seedA.as<int>();
     ck.seedB = I.seedB.as<int>();
     ck.minvec = I.minvec.as<int>();
@@ -198,6 +200,8 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.active = I.active.as<int>();
     ck.next_active = I.next_active.as<int>();
     ck.counters = I.counters.as<int>();
+    ck.thr = I.thr.as<int>(); ck.ub = I.ub.as<int>(); ck.t0 = I.t0.as<int>(); ck.resolved = I.resolved.as<int>();
+    ck.round = 0;
     rt::stream_sync(I.stream);
     return true;
 }
@@ -208,14 +212,14 @@ void Engine::run_staged() {
     rt::check(cudaSetDevice(I.device), "cudaSetDevice");
 #endif
     stats_.launches = stats_.fill_launches = stats_.jump_launches = 0;
-    stats_.layers_run = 0;
+    stats_.chains_run = stats_.rows_filled = stats_.rows_jumped = stats_.chains_started = 0;
+    stats_.layers_run = 0; stats_.rounds_run = 0;
+    stats_.jump_ms = stats_.fill_ms = 0;
     const int n_all = (int)I.list_all.size();
     if (n_all == 0) return;
     const size_t k1_smem = (size_t)K1_WARPS * MAX_ALPHABET * MAX_ALPHABET * sizeof(int);
-    const unsigned k1_grid = (unsigned)((n_all + K1_WARPS - 1) / K1_WARPS);
     rt::dev_memset(I.active.p, 0, I.npairs * 4, I.stream);
     rt::dev_memset(I.next_active.p, 0, I.npairs * 4, I.stream);
-    stats_.jump_ms = stats_.fill_ms = 0;
 #ifndef TSA_EMUL
     auto mark = [&](int k) { rt::check(cudaEventRecord(I.ev[k], I.stream), "cudaEventRecord"); };
     auto span = [&](int a, int b) { float ms = 0; rt::check(cudaEventSynchronize(I.ev[b]), "cudaEventSynchronize"); cudaEventElapsedTime(&ms, I.ev[a], I.ev[b]); return (double)ms; };
@@ -223,56 +227,75 @@ void Engine::run_staged() {
     auto mark = [&](int) {};
     auto span = [&](int, int) { return 0.0; };
 #endif
-    mark(0);
-    TSA_LAUNCH(k_primary_fill, dim3(k1_grid), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, I.d_list_all, n_all, 0);
-    mark(1);
-    stats_.launches++; stats_.fill_launches++;
-    if (!I.ts_enabled) { rt::stream_sync(I.stream); stats_.fill_ms += span(0, 1); return; }
-
+    auto fill = [&](const int* d_list, int cnt, int layer) {
+        TSA_LAUNCH(k_primary_fill, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
+        stats_.launches++; stats_.fill_launches++;
+    };
     int n_ts = 0;
     for (int c = 0; c < N_CLASS; c++) n_ts += (int)I.class_list[c].size();
-    if (n_ts == 0) { rt::stream_sync(I.stream); stats_.fill_ms += span(0, 1); return; }
-    bool fill_pending = true;   // events 0..1 bracket a fill that has not been read yet
     // the TS-enabled pairs are exactly the union of the class lists, which are contiguous after list_all
     const int* d_ts_list = I.d_class_list[0];
-    const unsigned fill_grid = (unsigned)((n_ts + K1_WARPS - 1) / K1_WARPS);
-    for (int layer = 0; layer < I.opt.max_layers; layer++) {
-        rt::dev_memset(I.counters.p, 0, 64, I.stream);
-        for (int off = 0; off < n_ts; off += 65535) {
-            const int cnt = std::min(65535, n_ts - off);
-            TSA_LAUNCH(k_clear_seeds, dim3(8, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, d_ts_list + off, cnt);
-            stats_.launches++;
-        }
-        mark(2);
-        for (int c = 0; c < N_CLASS; c++) {
-            const int cnt = (int)I.class_list[c].size();
-            if (!cnt) continue;
-            long long l = 0;
-            switch (CLASS_C[c]) {
-            case 3: launch_jump<3>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-            case 5: launch_jump<5>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-            case 9: launch_jump<9>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-            case 17: launch_jump<17>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-            default: launch_jump<33>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+    const unsigned ts_grid = (unsigned)((n_ts + 255) / 256);
+    I.ck.round = -1;
+    if (n_ts) { TSA_LAUNCH(k_resolve, dim3(ts_grid), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts, I.opt.first_threshold); stats_.launches++; }
+    I.ck.round = 0;
+    mark(0);
+    fill(I.d_list_all, n_all, 0);
+    mark(1);
+    if (!I.ts_enabled || n_ts == 0) { rt::stream_sync(I.stream); stats_.fill_ms += span(0, 1); return; }
+    bool fill_pending = true;   // events 0..1 bracket a fill that has not been read yet
+
+    for (int round = 0;; round++) {
+        I.ck.round = round;
+        if (round > 0) { mark(0); fill(d_ts_list, n_ts, 0); mark(1); fill_pending = true; }   // layer 0 again for the unresolved pairs
+        bool capped = false;
+        for (int layer = 0;; layer++) {
+            rt::dev_memset(I.counters.p, 0, 64, I.stream);
+            for (int off = 0; off < n_ts; off += 65535) {
+                const int cnt = std::min(65535, n_ts - off);
+                TSA_LAUNCH(k_clear_seeds, dim3(8, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, d_ts_list + off, cnt);
+                stats_.launches++;
             }
-            stats_.launches += l; stats_.jump_launches += l;
+            mark(2);
+            for (int c = 0; c < N_CLASS; c++) {
+                const int cnt = (int)I.class_list[c].size();
+                if (!cnt) continue;
+                long long l = 0;
+                switch (CLASS_C[c]) {
+                case 3: launch_jump<3>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+                case 5: launch_jump<5>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+                case 9: launch_jump<9>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+                case 17: launch_jump<17>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+                default: launch_jump<33>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+                }
+                stats_.launches += l; stats_.jump_launches += l;
+            }
+            mark(3);
+            TSA_LAUNCH(k_advance, dim3(ts_grid), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts);
+            stats_.launches++;
+            int h_counters[8] = {0};
+            rt::d2h(h_counters, I.counters.p, sizeof(h_counters), I.stream);
+            rt::stream_sync(I.stream);
+            stats_.chains_run += h_counters[1]; stats_.rows_filled += h_counters[2]; stats_.rows_jumped += h_counters[3]; stats_.chains_started += h_counters[4];
+            if (fill_pending) { stats_.fill_ms += span(0, 1); fill_pending = false; }
+            stats_.jump_ms += span(2, 3);
+            stats_.layers_run = std::max(stats_.layers_run, layer + 1);
+            if (h_counters[0] == 0) break;
+            if (layer + 1 >= I.opt.max_layers) { capped = true; break; }   // fetch_staged reports the still-active pairs
+            mark(0);
+            fill(d_ts_list, n_ts, layer + 1);
+            mark(1);
+            fill_pending = true;
         }
-        mark(3);
-        TSA_LAUNCH(k_advance, dim3((unsigned)((n_ts + 255) / 256)), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts);
+        stats_.rounds_run = round + 1;
+        if (capped) break;
+        rt::dev_memset(I.counters.p, 0, 64, I.stream);
+        TSA_LAUNCH(k_resolve, dim3(ts_grid), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts, 0);
         stats_.launches++;
-        int h_count = 0;
-        rt::d2h(&h_count, I.counters.p, 4, I.stream);
+        int h_counters[8] = {0};
+        rt::d2h(h_counters, I.counters.p, sizeof(h_counters), I.stream);
         rt::stream_sync(I.stream);
-        if (fill_pending) { stats_.fill_ms += span(0, 1); fill_pending = false; }
-        stats_.jump_ms += span(2, 3);
-        stats_.layers_run = layer + 1;
-        if (h_count == 0) break;
-        if (layer + 1 >= I.opt.max_layers) break;
-        mark(0);
-        TSA_LAUNCH(k_primary_fill, dim3(fill_grid), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_ts_list, n_ts, layer + 1);
-        mark(1);
-        fill_pending = true;
-        stats_.launches++; stats_.fill_launches++;
+        if (h_counters[5] == 0) break;
     }
 }
 
@@ -332,16 +355,16 @@ TSA_KERNEL void k_addmin_probe(uint32_t* out, int iters, int packed) {
     const uint32_t t = (uint32_t)(blockIdx.x * blockDim.x + threadIdx.x);
 #pragma unroll
     for (int k = 0; k < 8; k++) a[k] = (t * 2654435761u + (uint32_t)k * 40503u) & 0x0fff0fffu;
-    const uint32_t b = (t & 7u) | ((t & 3u) << 16), c = 0x3fff3fffu;
+    const uint32_t b = (t & 7u) | ((t & 3u) << 16);
     if (packed) {
         for (int i = 0; i < iters; i++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) a[k] = addmin_s16x2(a[k], b, c ^ a[(k + 1) & 7]);
+            for (int k = 0; k < 8; k++) a[k] = addmin_s16x2(a[k], b, a[(k + 3) & 7]);
         }
     } else {
         for (int i = 0; i < iters; i++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) a[k] = (uint32_t)addmin_s32((int)a[k], (int)b, (int)(c ^ a[(k + 1) & 7]));
+            for (int k = 0; k < 8; k++) a[k] = (uint32_t)addmin_s32((int)a[k], (int)b, (int)a[(k + 3) & 7]);
         }
     }
     uint32_t r = 0;
@@ -361,7 +384,6 @@ bool measure_addmin_peak(int device, double* s16x2_lane_ops_per_s, double* s32_l
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int iters = 4096, threads = 256, blocks = prop.multiProcessorCount * 8;
-    // the xor feeding operand c is one extra ALU op per add-min: count only the add-min lanes (a lower bound on peak)
     for (int packed = 1; packed >= 0; packed--) {
         double best = 0;
         for (int rep = 0; rep < 4; rep++) {

@@ -13,6 +13,7 @@ namespace tsa {
 struct AlignOptions {
     bool no_ts = false;            // --no-ts: MaxTemplateSwitchCount(0), strategies/template_switch_count.rs:41-63
     int max_layers = 64;           // cap on the number of template switches per alignment
+    int first_threshold = 12;      // first pruning threshold of the iterative deepening (doubles per round)
     size_t chunk_bytes = (size_t)6 << 30;  // HBM budget of one resident chunk of pairs
 };
 
@@ -42,8 +43,10 @@ struct EngineStats {
     long long launches = 0;        // kernels launched by the last run()
     long long fill_launches = 0, jump_launches = 0;
     int layers_run = 0;            // jump rounds of the last run (max over chunks)
+    int rounds_run = 0;            // deepening rounds of the last run
     double jump_ms = 0, fill_ms = 0;  // device time of the two kernel families (CUDA events; 0 in the emulator)
     long long h2d_bytes = 0, d2h_bytes = 0;
+    long long chains_started = 0, chains_run = 0, rows_filled = 0, rows_jumped = 0;  // jump-kernel work of the last run
 };
 
 class Engine {

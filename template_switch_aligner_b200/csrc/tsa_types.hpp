@@ -21,6 +21,8 @@ struct KindDesc {
     int table;             // 1 = secondary forward, 2 = secondary reverse edit table
     int n_oc;              // effective first-offset cost pieces (forward quirk folded in)
     Piece oc[MAX_PIECES];
+    int min_open;          // cheapest gap-open cost of this kind's secondary edit table
+    int oc_lo, oc_hi, oc_skip0; // hull of the reachable first offsets; oc_skip0: offset 0 is not reachable (forward kinds)
     int n_apg;             // anti-primary-gap pieces of this direction
     Piece apg[MAX_PIECES];
     int min_rest_nolc;     // min over finite (oc + ldc + apg): lower bound of everything but base, length and inner
@@ -55,6 +57,14 @@ struct PairMeta {
     long long scr;           // int offset of the column-tiling scratch of the primary fill: 3 * (n+1)
 };
 
+// Traceback code of one cell of one layer (written by k_primary_fill, read by k_traceback).
+constexpr int DIR_N_DIAG = 1;     // N state came from the diagonal move (else: reentry seed / root)
+constexpr int DIR_DL_EXT = 2;     // Dl state extended a deletion (else: opened from N or I of the cell above)
+constexpr int DIR_I_EXT = 4;      // I state extended an insertion (else: opened from N or Dl of the cell to the left)
+constexpr int DIR_M_SHIFT = 3;    // bits 3-4: cheapest state of the cell: 0 = N, 1 = Dl, 2 = I (ties in that order)
+constexpr int DIR_NI_IS_I = 32;   // min(N, I) is I
+constexpr int DIR_ND_IS_DL = 64;  // min(N, Dl) is Dl
+
 // Everything a kernel needs about the resident chunk of pairs.
 struct Chunk {
     const PairMeta* pairs;
@@ -63,6 +73,7 @@ struct Chunk {
     const int* lc;           // dense length costs (cfg->n_lc entries)
     int16_t* D;              // [pair][i][j]  min_g cost of layer k at flank == L_f, clamped to INF16
     int16_t* DT;             // [pair][j][i]  the same, transposed (primary = query kinds read rows of it)
+    uint8_t* dir;            // [pair][i][j]  traceback codes of the layer being filled (DIR_* bits), or null
     int* seedA;              // [pair][i][j]  reentry seeds of layer k+1 written by primary = reference kinds
     int* seedB;              // [pair][j][i]  reentry seeds written by primary = query kinds
     int* minvec;             // rowmin / colmin of D
@@ -71,7 +82,12 @@ struct Chunk {
     int* best_layer;         // [pair] first layer that reached `best`
     int* active;             // [pair] layer k has seeds below best (fill it, then jump from it)
     int* next_active;        // [pair] set by the jump kernel when it writes a seed below best
-    int* counters;           // [0] number of pairs with next_active
+    int* thr;                // [pair] exclusive cost threshold of the current deepening round (see k_resolve)
+    int* ub;                 // [pair] pruning bound: candidates with cost >= ub are dropped (<= thr, tightened as targets are found)
+    int* t0;                 // [pair] target cost of layer 0 (no template switch)
+    int* resolved;           // [pair] optimum proven
+    int round;               // deepening round (0 = first)
+    int* counters;           // [0] pairs with next_active, [1..4] work statistics, [5] unresolved pairs
 };
 
 }  // namespace tsa
