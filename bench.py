@@ -199,11 +199,14 @@ def run_ours(args):
     t0 = time.perf_counter()
     jump_ms = fill_ms = 0.0
     launches = jump_launches = 0
+    work = {"chains_started": 0, "chains_run": 0, "rows_filled": 0, "rows_jumped": 0}
     for _ in range(args.steps):
         staged.run()
         tm, st = staged.timing(), staged.stats()
         jump_ms += tm["jump_ms"]; fill_ms += tm["fill_ms"]
         launches += st["launches"]; jump_launches += st["jump_launches"]
+        for key in work:
+            work[key] += tm[key]
     barrier()
     elapsed = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
@@ -265,7 +268,11 @@ def run_ours(args):
             "pairs_per_s": batch * world * args.steps / elapsed,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": stats["h2d_bytes"], "d2h_bytes_per_step": stats["d2h_bytes"],
                     "pairs_per_s": batch * world * e2e_steps / e2e_elapsed, "steps": e2e_steps},
-            "gpu_launches": launches, "layers_per_step": stats["layers"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": launches, "layers_per_step": stats["layers"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "work": {**{k: v / args.steps for k, v in work.items()},
+                     "note": "per step: chain pairs started / surviving chain-level pruning, chain rows filled (2 chains x 160 columns each), "
+                             "rows whose jump-in/jump-out was evaluated; the dense formula of SURVEY 8(d) assumes 99 rows per chain"},
+            "alignments": "every pair returns its run-length encoded alignment (traceback kernel inside the timed step)"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

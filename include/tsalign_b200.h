@@ -37,7 +37,8 @@ enum {
     TSA_ERR_INVALID_CHAR = 7,       /* a sequence character is not in the alphabet (align.rs:389-405; the facade panics) */
     TSA_ERR_INVALID_RANGE = 8,      /* offset > limit or limit > length */
     TSA_ERR_UNSUPPORTED = 9,        /* cost model outside the kernels' limits (see message) */
-    TSA_ERR_ARGUMENT = 10
+    TSA_ERR_ARGUMENT = 10,
+    TSA_ERR_INTERNAL = 11           /* a consistency check of the library failed (never a wrong result) */
 };
 
 /* ---- alphabets: tsalign/src/align.rs:80-81,288-295 (-a/--alphabet) -------------------------------------- */
@@ -63,6 +64,8 @@ typedef struct {
     uint64_t memory_limit;         /* --memory-limit in bytes, UINT64_MAX = none: bounds the resident HBM chunk */
     int32_t max_template_switches; /* 0 = default (64) */
     int32_t first_threshold;       /* 0 = default (12): first pruning threshold of the iterative deepening; tuning only, never changes results */
+    int32_t no_traceback;          /* 1 = costs only (ops == NULL) */
+    int32_t reserved;
 } tsa_options;
 
 /* ---- one alignment problem: the arguments of Aligner::align (configurable_a_star_align.rs:214-236) ------ */

@@ -15,7 +15,7 @@ TSA_OK = 0
 STATUS_NAMES = {
     0: "TSA_OK", 1: "TSA_ERR_NO_DEVICE", 2: "TSA_ERR_CONFIG_PARSE", 3: "TSA_ERR_NOT_V_SHAPED_RQQR",
     4: "TSA_ERR_NOT_V_SHAPED_RRQQ", 5: "TSA_ERR_NOT_V_SHAPED_LENDIFF", 6: "TSA_ERR_ALPHABET", 7: "TSA_ERR_INVALID_CHAR",
-    8: "TSA_ERR_INVALID_RANGE", 9: "TSA_ERR_UNSUPPORTED", 10: "TSA_ERR_ARGUMENT",
+    8: "TSA_ERR_INVALID_RANGE", 9: "TSA_ERR_UNSUPPORTED", 10: "TSA_ERR_ARGUMENT", 11: "TSA_ERR_INTERNAL",
 }
 RESULT_NAMES = ["FoundTarget", "ExceededCostLimit", "ExceededMemoryLimit", "NoTarget"]
 ALPHABETS = {"dna": 0, "dna-n": 1, "rna": 2, "rna-n": 3, "dna-iupac": 4, "rna-iupac": 5}
@@ -34,7 +34,7 @@ EXPORTS = [
 
 class TsaOptions(C.Structure):
     _fields_ = [("no_ts", C.c_int32), ("device", C.c_int32), ("cost_limit", C.c_uint64), ("memory_limit", C.c_uint64),
-                ("max_template_switches", C.c_int32), ("first_threshold", C.c_int32)]
+                ("max_template_switches", C.c_int32), ("first_threshold", C.c_int32), ("no_traceback", C.c_int32), ("reserved", C.c_int32)]
 
 
 class TsaPair(C.Structure):

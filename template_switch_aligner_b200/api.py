@@ -48,7 +48,7 @@ class TemplateSwitchExitOp:
 
 
 AlignmentOp = Union[SimpleAlignmentOp, TemplateSwitchEntranceOp, TemplateSwitchExitOp]
-_INVALID_RANGE = {"min_start": 127, "max_start": -128, "min_end": 127, "max_end": -128}
+_INVALID_RANGE = {"min_start": 1, "max_start": -1, "min_end": 1, "max_end": -1}  # EqualCostRange::new_invalid()
 
 
 class Config:
@@ -105,7 +105,7 @@ def _make_pairs(pairs: Sequence[tuple]):
     return arr, keep
 
 
-def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0) -> TsaOptions:
+def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0, traceback=True) -> TsaOptions:
     o = TsaOptions()
     o.no_ts = int(bool(no_ts))
     o.device = device
@@ -113,6 +113,7 @@ def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_temp
     o.memory_limit = U64_MAX if memory_limit is None else int(memory_limit)
     o.max_template_switches = max_template_switches
     o.first_threshold = first_threshold
+    o.no_traceback = 0 if traceback else 1
     return o
 
 
@@ -223,7 +224,7 @@ class Aligner:
     def __init__(self, *, no_ts: bool = False, min_length_strategy: str = "lookahead", chaining_strategy: str = "none",
                  total_length_strategy: str = "maximise", costs: Optional[str] = None,
                  costs_file: Optional[Union[str, pathlib.Path]] = None, alphabet: str = "dna-n", device: int = 0,
-                 first_threshold: int = 0, lib=None) -> None:
+                 first_threshold: int = 0, traceback: bool = True, lib=None) -> None:
         if costs is not None and costs_file is not None:
             raise ValueError("Provide at most one of 'costs' or 'costs_file'.")
         if min_length_strategy not in _MIN_LENGTH:
@@ -237,6 +238,7 @@ class Aligner:
         self._lib = lib or _lib.default()
         self.no_ts = bool(no_ts)
         self.device = device
+        self.traceback = bool(traceback)        # False: optimal costs only
         self.first_threshold = first_threshold  # tuning of the exact pruning only; results do not depend on it
         self.config = Config(costs, alphabet, lib=self._lib)
 
@@ -246,7 +248,7 @@ class Aligner:
         arr, keep = _make_pairs(pairs)
         res = (TsaResult * max(1, len(pairs)))()
         err = C.create_string_buffer(512)
-        opt = _options(self.no_ts, self.device, cost_limit, memory_limit, first_threshold=self.first_threshold)
+        opt = _options(self.no_ts, self.device, cost_limit, memory_limit, first_threshold=self.first_threshold, traceback=self.traceback)
         rc = self._lib.tsa_align_batch(self.config._h, C.byref(opt), arr, len(pairs), res, err, len(err))
         if rc != 0:
             raise TsaError(rc, err.value.decode(errors="replace"))
@@ -274,7 +276,7 @@ class Aligner:
 
 def align(reference: object, query: object, **kwargs: object) -> Optional[Alignment]:
     """One-call convenience wrapper (mirror of tsalign.align)."""
-    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib", "first_threshold")}
+    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib", "first_threshold", "traceback")}
     align_kwargs = {k: v for k, v in kwargs.items() if k not in aligner_kwargs}
     return Aligner(**aligner_kwargs).align(reference, query, **align_kwargs)
 
@@ -289,7 +291,7 @@ class StagedBatch:
         arr, keep = _make_pairs(pairs)
         status = C.c_int(0)
         err = C.create_string_buffer(512)
-        opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit, first_threshold=aligner.first_threshold)
+        opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit, first_threshold=aligner.first_threshold, traceback=aligner.traceback)
         self._h = self._lib.tsa_batch_create(aligner.config._h, C.byref(opt), arr, self.n, C.byref(status), err, len(err))
         if not self._h:
             raise TsaError(status.value, err.value.decode(errors="replace"))

@@ -74,6 +74,42 @@ void encode_pairs(const HostConfig& cfg, const tsa_pair* pairs, size_t n, Encode
     for (size_t i = 0; i < n; i++) if (e.pair_status[i] == TSA_OK) { e.live.push_back(i); e.views.push_back(all[i]); }
 }
 
+// Unit ops -> the run-length encoded list the reference emits (a_star_aligner.rs:100-122, alignment_type.rs:101-139).
+// Entrance / exit multiplicities are the artefacts of the reference's +-1 walks: |first_offset| + 1
+// (reverse) or |first_offset| (forward) for an entrance, |length_difference| + 1 for an exit.
+void assemble_ops(tsa_result& r, const PairCost& pc) {
+    std::vector<tsa_op> out;
+    size_t rec = 0;
+    for (uint8_t u : pc.ops) {
+        if (u == 12 || u == 13) {
+            if (rec >= pc.recs.size() + (u == 13 ? 1 : 0) && u == 12) break;
+            const TsRecord& t = pc.recs[u == 12 ? rec : rec - 1];
+            tsa_op op;
+            memset(&op, 0, sizeof(op));
+            if (u == 12) {
+                const int d = t.kind >> 2;
+                const long long o = t.first_offset;
+                op.type = TSA_OP_TS_ENTRANCE; op.primary = (t.kind >> 1) & 1; op.secondary = t.kind & 1; op.direction = d;
+                op.value = o; op.count = d == 1 ? std::llabs(o) + 1 : std::llabs(o);
+                rec++;
+            } else {
+                const long long ld = (long long)t.anti_primary_gap - t.length;
+                op.type = TSA_OP_TS_EXIT; op.value = t.anti_primary_gap; op.count = std::llabs(ld) + 1;
+            }
+            out.push_back(op);
+            continue;
+        }
+        if (!out.empty() && out.back().type == (int32_t)u) { out.back().count++; continue; }
+        tsa_op op;
+        memset(&op, 0, sizeof(op));
+        op.type = u; op.count = 1;
+        out.push_back(op);
+    }
+    r.n_ops = out.size();
+    r.ops = (tsa_op*)malloc(sizeof(tsa_op) * std::max<size_t>(1, out.size()));
+    memcpy(r.ops, out.data(), sizeof(tsa_op) * out.size());
+}
+
 void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
     memset(&r, 0, sizeof(r));
     switch (pc.status) {
@@ -84,6 +120,8 @@ void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
             r.result_type = TSA_EXCEEDED_COST_LIMIT; r.cost = opt.cost_limit;
         } else {
             r.result_type = TSA_FOUND_TARGET; r.cost = (uint64_t)pc.cost; r.template_switches = pc.layers;
+            if (pc.trace_status == TRACE_OK) assemble_ops(r, pc);
+            else if (pc.trace_status != TRACE_SKIPPED) { r.status = TSA_ERR_INTERNAL; snprintf(r.message, sizeof(r.message), "traceback failed (code %d)", pc.trace_status); }
         }
         break;
     case PAIR_NO_TARGET: r.status = TSA_OK; r.result_type = TSA_NO_TARGET; break;
@@ -100,6 +138,8 @@ AlignOptions engine_options(const tsa_options& o) {
     a.no_ts = o.no_ts != 0;
     if (o.max_template_switches > 0) a.max_layers = o.max_template_switches;
     if (o.first_threshold > 0) a.first_threshold = o.first_threshold;
+    a.traceback = o.no_traceback == 0;
+    if (a.traceback) a.max_layers = std::min(a.max_layers, (int)MAX_TRACE_LAYERS);
     if (o.memory_limit != UINT64_MAX) a.chunk_bytes = (size_t)std::max<uint64_t>(o.memory_limit, (uint64_t)1 << 20);
     return a;
 }

@@ -67,6 +67,11 @@ void launch_jump(const Chunk& ck, const int* d_list, int n_list, int max_len, in
 struct Engine::Impl {
     int device = 0;
     cudaStream_t stream = 0;
+    std::vector<DevBuf*> dirL, DL;       // per-layer traceback codes / D matrices (traceback only)
+    DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows;
+    std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
+    size_t cells = 0, ops_total = 0;
+    int max_recs = 0;
     DevBuf cfg, lc, meta, seq, D, DT, seedA, seedB, minvec, scratch, best, best_layer, active, next_active, counters, lists, thr, ub, t0, resolved;
     std::vector<PairMeta> metas;
     std::vector<uint8_t> seqpool;
@@ -111,6 +116,8 @@ Engine::Engine(const HostConfig& cfg, int device) : impl_(new Impl), host_(cfg) 
 }
 
 Engine::~Engine() {
+    for (DevBuf* b : impl_->dirL) delete b;
+    for (DevBuf* b : impl_->DL) delete b;
 #ifndef TSA_EMUL
     if (ok_) {
         cudaSetDevice(impl_->device);
@@ -150,13 +157,25 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
             int cls = -1;
             for (int c = 0; c < N_CLASS; c++) if (W <= 32 * CLASS_C[c]) { cls = c; break; }
             if (cls < 0) { I.status[i] = PAIR_ERR_TOO_LONG; continue; }
-            cells += (size_t)(pv.n + 1) * (pv.m + 1);
             I.class_list[cls].push_back((int)i);
             I.class_maxlen[cls] = std::max(I.class_maxlen[cls], W - 1);
         }
+        if (I.ts_enabled || opt.traceback) cells += (size_t)(pv.n + 1) * (pv.m + 1);
         I.list_all.push_back((int)i);
     }
-    size_t need = seq_bytes + cells * 12 + vec * 4 + scr * 4 + n * (sizeof(PairMeta) + 32);
+    I.cells = cells;
+    I.max_recs = std::min(opt.max_layers, MAX_TRACE_LAYERS);
+    if (opt.traceback) {
+        I.h_ops_off.assign(n, 0); I.h_ops_cap.assign(n, 0);
+        size_t off = 0;
+        for (size_t i = 0; i < n; i++) {
+            I.h_ops_off[i] = (long long)off;
+            I.h_ops_cap[i] = 3 * (pairs[i].n + pairs[i].m) + 256;
+            off += (size_t)I.h_ops_cap[i];
+        }
+        I.ops_total = off;
+    }
+    size_t need = seq_bytes + cells * (I.ts_enabled ? 12 : 0) + (opt.traceback ? cells * 3 + I.ops_total : 0) + vec * 4 + scr * 4 + n * (sizeof(PairMeta) + 32);
     if (need > opt.chunk_bytes && n > 1) return false;
     I.seqpool.resize(seq_bytes);
     for (size_t i = 0; i < n; i++) {
@@ -171,6 +190,12 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.counters.ensure(64);
     I.thr.ensure(n * 4); I.ub.ensure(n * 4); I.t0.ensure(n * 4); I.resolved.ensure(n * 4);
     if (I.ts_enabled) { I.D.ensure(cells * 2); I.DT.ensure(cells * 2); I.seedA.ensure(cells * 4); I.seedB.ensure(cells * 4); }
+    if (opt.traceback) {
+        I.ops.ensure(I.ops_total); I.ops_off.ensure(n * 8); I.ops_cap.ensure(n * 4); I.ops_len.ensure(n * 4);
+        I.recs.ensure(n * (size_t)I.max_recs * sizeof(TsRecord)); I.n_recs.ensure(n * 4); I.tstatus.ensure(n * 4);
+        rt::h2d(I.ops_off.p, I.h_ops_off.data(), n * 8, I.stream);
+        rt::h2d(I.ops_cap.p, I.h_ops_cap.data(), n * 4, I.stream);
+    }
     // pair lists: all, then one per class
     std::vector<int> flat = I.list_all;
     size_t off_class[N_CLASS];
@@ -228,6 +253,13 @@ void Engine::run_staged() {
     auto span = [&](int, int) { return 0.0; };
 #endif
     auto fill = [&](const int* d_list, int cnt, int layer) {
+        if (I.opt.traceback) {
+            // keep every layer's traceback codes (and D, the template-switch entrance costs) until the traceback
+            while ((int)I.dirL.size() <= layer) { I.dirL.push_back(new DevBuf); I.DL.push_back(new DevBuf); }
+            I.dirL[layer]->ensure(I.cells);
+            I.ck.dir = I.dirL[layer]->as<uint8_t>();
+            if (I.ts_enabled) { I.DL[layer]->ensure(I.cells * 2); I.ck.D = I.DL[layer]->as<int16_t>(); }
+        }
         TSA_LAUNCH(k_primary_fill, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
         stats_.launches++; stats_.fill_launches++;
     };
@@ -242,7 +274,10 @@ void Engine::run_staged() {
     mark(0);
     fill(I.d_list_all, n_all, 0);
     mark(1);
-    if (!I.ts_enabled || n_ts == 0) { rt::stream_sync(I.stream); stats_.fill_ms += span(0, 1); return; }
+    if (!I.ts_enabled || n_ts == 0) {
+        rt::dev_memset(I.active.p, 0, I.npairs * 4, I.stream);   // no jump follows: nothing stays active
+        rt::stream_sync(I.stream); stats_.fill_ms += span(0, 1); run_trace(); return;
+    }
     bool fill_pending = true;   // events 0..1 bracket a fill that has not been read yet
 
     for (int round = 0;; round++) {
@@ -297,6 +332,64 @@ void Engine::run_staged() {
         rt::stream_sync(I.stream);
         if (h_counters[5] == 0) break;
     }
+    run_trace();
+}
+
+template <int C>
+static void launch_trace(const Chunk& ck, const TraceLayers& tl, TraceOut to, DevBuf& rows, const int* d_list, int n_list, int rows_max, int A,
+                         cudaStream_t stream, long long& launches) {
+    if (n_list <= 0) return;
+    const int warps = jump_warps(A, C);
+    const size_t smem = jump_smem_per_warp(A, C) * warps;
+#ifndef TSA_EMUL
+    static bool attr_set = false;
+    if (!attr_set) {
+        rt::check(cudaFuncSetAttribute(k_traceback<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
+        attr_set = true;
+    }
+#endif
+    const long long stride = (long long)(rows_max + 1) * 3 * 32 * C;   // shorts per warp
+    const long long budget = (long long)1 << 29;                        // 1 GiB of shorts-pairs scratch per slice
+    const int slice = (int)std::max<long long>(warps, std::min<long long>(n_list, budget / std::max<long long>(1, stride)));
+    rows.ensure((size_t)slice * (size_t)stride * 2);
+    to.rows = rows.as<int16_t>();
+    to.rows_stride = stride;
+    for (int off = 0; off < n_list; off += slice) {
+        const int cnt = std::min(slice, n_list - off);
+        TSA_LAUNCH(k_traceback<C>, dim3((unsigned)((cnt + warps - 1) / warps)), dim3(32 * warps), smem, stream, ck, tl, to, d_list + off, cnt);
+        launches++;
+    }
+}
+
+void Engine::run_trace() {
+    Impl& I = *impl_;
+    if (!I.opt.traceback) return;
+    TraceLayers tl;
+    memset(&tl, 0, sizeof(tl));
+    for (size_t k = 0; k < I.dirL.size() && k <= (size_t)MAX_TRACE_LAYERS; k++) { tl.dir[k] = I.dirL[k]->as<uint8_t>(); tl.D[k] = I.DL[k]->as<int16_t>(); }
+    TraceOut to;
+    memset(&to, 0, sizeof(to));
+    to.ops = I.ops.as<uint8_t>(); to.ops_off = I.ops_off.as<long long>(); to.ops_cap = I.ops_cap.as<int>(); to.ops_len = I.ops_len.as<int>();
+    to.recs = I.recs.as<TsRecord>(); to.max_recs = I.max_recs; to.n_recs = I.n_recs.as<int>(); to.status = I.tstatus.as<int>();
+    long long l = 0;
+    if (!I.ts_enabled) {
+        launch_trace<3>(I.ck, tl, to, I.rows, I.d_list_all, (int)I.list_all.size(), 0, dev_.A, I.stream, l);
+    } else {
+        for (int c = 0; c < N_CLASS; c++) {
+            const int cnt = (int)I.class_list[c].size();
+            if (!cnt) continue;
+            const int rows_max = std::min(dev_.lmax, I.class_maxlen[c]);
+            switch (CLASS_C[c]) {
+            case 3: launch_trace<3>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            case 5: launch_trace<5>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            case 9: launch_trace<9>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            case 17: launch_trace<17>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            default: launch_trace<33>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            }
+        }
+    }
+    stats_.launches += l; stats_.trace_launches = l;
+    rt::stream_sync(I.stream);
 }
 
 void Engine::fetch_staged(PairCost* out) {
@@ -321,6 +414,27 @@ void Engine::fetch_staged(PairCost* out) {
         pc.status = PAIR_OK;
         pc.cost = I.h_best[i];
         pc.layers = I.h_layer[i];
+    }
+    if (!I.opt.traceback) return;
+    std::vector<int> len(n), nrec(n), tst(n);
+    std::vector<uint8_t> ops(I.ops_total);
+    std::vector<TsRecord> recs(n * (size_t)I.max_recs);
+    rt::d2h(len.data(), I.ops_len.p, n * 4, I.stream);
+    rt::d2h(nrec.data(), I.n_recs.p, n * 4, I.stream);
+    rt::d2h(tst.data(), I.tstatus.p, n * 4, I.stream);
+    rt::d2h(ops.data(), I.ops.p, I.ops_total, I.stream);
+    rt::d2h(recs.data(), I.recs.p, recs.size() * sizeof(TsRecord), I.stream);
+    rt::stream_sync(I.stream);
+    stats_.d2h_bytes += (long long)(n * 12 + I.ops_total + recs.size() * sizeof(TsRecord));
+    for (size_t i = 0; i < n; i++) {
+        PairCost& pc = out[i];
+        if (pc.status != PAIR_OK) continue;
+        pc.trace_status = tst[i];
+        if (tst[i] != TRACE_OK) continue;
+        const uint8_t* src = ops.data() + I.h_ops_off[i];
+        pc.ops.assign(std::reverse_iterator<const uint8_t*>(src + len[i]), std::reverse_iterator<const uint8_t*>(src));
+        const TsRecord* rs = recs.data() + i * (size_t)I.max_recs;
+        pc.recs.assign(std::reverse_iterator<const TsRecord*>(rs + nrec[i]), std::reverse_iterator<const TsRecord*>(rs));
     }
 }
 

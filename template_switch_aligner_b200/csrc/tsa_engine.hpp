@@ -13,6 +13,7 @@ namespace tsa {
 struct AlignOptions {
     bool no_ts = false;            // --no-ts: MaxTemplateSwitchCount(0), strategies/template_switch_count.rs:41-63
     int max_layers = 64;           // cap on the number of template switches per alignment
+    bool traceback = true;         // produce alignments (ops), not only costs
     int first_threshold = 12;      // first pruning threshold of the iterative deepening (doubles per round)
     size_t chunk_bytes = (size_t)6 << 30;  // HBM budget of one resident chunk of pairs
 };
@@ -37,11 +38,14 @@ struct PairCost {
     int status = PAIR_OK;
     int64_t cost = 0;              // optimal cost (status == PAIR_OK)
     int layers = 0;                // number of template switches on the optimal path found (first layer reaching cost)
+    int trace_status = TRACE_SKIPPED;
+    std::vector<uint8_t> ops;      // unit ops in path order (TraceOut encoding), when traceback was requested
+    std::vector<TsRecord> recs;    // template switches in path order
 };
 
 struct EngineStats {
     long long launches = 0;        // kernels launched by the last run()
-    long long fill_launches = 0, jump_launches = 0;
+    long long fill_launches = 0, jump_launches = 0, trace_launches = 0;
     int layers_run = 0;            // jump rounds of the last run (max over chunks)
     int rounds_run = 0;            // deepening rounds of the last run
     double jump_ms = 0, fill_ms = 0;  // device time of the two kernel families (CUDA events; 0 in the emulator)
@@ -68,6 +72,7 @@ public:
     bool stage(const PairView* pairs, size_t n, const AlignOptions& opt);
     void run_staged();
     void fetch_staged(PairCost* out);
+    void run_trace();
 
     const EngineStats& stats() const { return stats_; }
     static size_t bytes_per_pair(int n, int m);

@@ -90,4 +90,29 @@ struct Chunk {
     int* counters;           // [0] pairs with next_active, [1..4] work statistics, [5] unresolved pairs
 };
 
+// ---- traceback ------------------------------------------------------------------------------------------------
+constexpr int MAX_TRACE_LAYERS = 64;
+// Per-layer matrices kept for the traceback (layer k of every pair at the pair's `mat` offset).
+struct TraceLayers {
+    const uint8_t* dir[MAX_TRACE_LAYERS + 1];
+    const int16_t* D[MAX_TRACE_LAYERS + 1];
+};
+// One template switch of an alignment, in traceback order (last switch first).
+struct TsRecord { int kind; int first_offset; int anti_primary_gap; int length; };
+enum { TRACE_OK = 0, TRACE_ERR_OVERFLOW = 1, TRACE_ERR_NO_SOURCE = 2, TRACE_ERR_WALK = 3, TRACE_SKIPPED = 4 };
+// Unit ops are written back to front, one byte each: 0..3 primary (insertion, deletion, substitution, match),
+// 8..11 secondary (same order), 12 = template switch entrance, 13 = exit (payload in the TsRecord list).
+struct TraceOut {
+    uint8_t* ops;            // [pair] at ops_off: capacity ops_cap
+    const long long* ops_off;
+    const int* ops_cap;
+    int* ops_len;            // [pair]
+    TsRecord* recs;          // [pair][max_recs]
+    int max_recs;
+    int* n_recs;             // [pair]
+    int* status;             // [pair] TRACE_*
+    int16_t* rows;           // chain rows scratch: one block of rows_stride shorts per warp of the launch
+    long long rows_stride;
+};
+
 }  // namespace tsa

@@ -1,0 +1,342 @@
+// tsalign_cli.cpp -- `tsalign-b200 align ...`: drop-in for the reference's `tsalign align` (default method
+// a-star-template-switch) on top of the C ABI.  Mirrors tsalign/src/align.rs:57-432 (flags, input handling order:
+// parse FASTA -> drop skip characters -> upper-case -> ranges -> alphabet check), align/fasta_parser.rs:24-174,
+// util.rs:14-28 (config directory), the stdout block of alignment_result.rs:736-777 and the TOML layout of
+// alignment_result.rs:32-81 as written by align/template_switch_distance_type_selectors.rs:442-449.
+//
+// Not done by this build (accepted, reported on stderr): extend_beyond_range / equal-cost ranges post-processing
+// (alignment_result.rs:247-573); `show`, `preprocess` and the other alignment methods.
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "tsalign_b200.h"
+
+namespace {
+
+struct Record { std::string id, comment, seq; };
+
+[[noreturn]] void die(const std::string& msg, int code = 1) {
+    fprintf(stderr, "Error: %s\n", msg.c_str());
+    exit(code);
+}
+
+// align/fasta_parser.rs:24-174
+std::vector<Record> parse_fasta(const std::string& path) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) die("Unable to open input file \"" + path + "\"");
+    std::stringstream ss; ss << in.rdbuf();
+    const std::string text = ss.str();
+    std::vector<Record> recs;
+    size_t pos = 0;
+    bool newline = true;
+    for (; pos < text.size(); pos++) {   // FileStart
+        char c = text[pos];
+        if (c == '\n' || c == '\r') newline = true;
+        else if (c == '>') { if (!newline) die("First fasta record is not preceded by a newline character"); break; }
+        else { newline = false; if (!isspace((unsigned char)c)) die(std::string("Found non-whitespace character before first fasta record: ") + c); }
+    }
+    if (pos >= text.size()) die("Input file \"" + path + "\" contains no fasta record");
+    while (pos < text.size()) {
+        Record r;
+        pos++;  // '>'
+        while (pos < text.size() && text[pos] != '\n' && text[pos] != '\r' && !isspace((unsigned char)text[pos])) r.id.push_back(text[pos++]);
+        if (pos < text.size() && text[pos] != '\n' && text[pos] != '\r') {
+            pos++;  // the whitespace that ends the id
+            while (pos < text.size() && text[pos] != '\n' && text[pos] != '\r') r.comment.push_back(text[pos++]);
+        }
+        newline = false;
+        for (; pos < text.size(); pos++) {
+            char c = text[pos];
+            if (c == '\n' || c == '\r') newline = true;
+            else if (c == '>' && newline) break;
+            else { r.seq.push_back(c); newline = false; }
+        }
+        recs.push_back(r);
+    }
+    return recs;
+}
+
+std::string fmt_f64(double v) {  // Rust `{}` for f64: shortest round-trip, always with a fractional part
+    if (std::isnan(v)) return "nan";
+    if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
+    char buf[64];
+    auto res = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::fixed);
+    std::string s(buf, res.ptr);
+    // fixed shortest can be long for tiny values; fall back to general when it helps
+    auto res2 = std::to_chars(buf, buf + sizeof(buf), v);
+    std::string g(buf, res2.ptr);
+    if (g.find('e') == std::string::npos) s = g;
+    if (s.find('.') == std::string::npos) s += ".0";
+    return s;
+}
+
+std::string toml_string(const std::string& s) {
+    std::string out = "\"";
+    for (char c : s) {
+        if (c == '"' || c == '\\') { out.push_back('\\'); out.push_back(c); }
+        else if (c == '\n') out += "\\n";
+        else if (c == '\t') out += "\\t";
+        else out.push_back(c);
+    }
+    return out + "\"";
+}
+
+const char* const OP_NAMES[] = {"PrimaryInsertion", "PrimaryDeletion", "PrimarySubstitution", "PrimaryMatch", "PrimaryFlankInsertion", "PrimaryFlankDeletion",
+                                "PrimaryFlankSubstitution", "PrimaryFlankMatch", "SecondaryInsertion", "SecondaryDeletion", "SecondarySubstitution", "SecondaryMatch"};
+
+std::string cigar(const tsa_result& r) {  // alignment.rs:95-110, template_switch_distance/display.rs:8-41
+    std::string out;
+    for (size_t i = 0; i < r.n_ops; i++) {
+        const tsa_op& op = r.ops[i];
+        if (op.type == TSA_OP_TS_ENTRANCE) {
+            out += std::string("[TS") + "RQ"[op.primary] + "RQ"[op.secondary] + "FR"[op.direction] + ":[-]:[-]:" + std::to_string(op.value) + ":";
+        } else if (op.type == TSA_OP_TS_EXIT) {
+            out += ":" + std::to_string(op.value) + "]";
+        } else {
+            out += std::to_string(op.count) + "IDX="[op.type & 3];
+        }
+    }
+    return out;
+}
+
+std::string complement_text(const std::string& s, bool rna) {
+    std::string out(s.rbegin(), s.rend());
+    for (char& c : out) {
+        switch (c) {
+        case 'A': c = rna ? 'U' : 'T'; break; case 'T': case 'U': c = 'A'; break; case 'C': c = 'G'; break; case 'G': c = 'C'; break;
+        case 'R': c = 'Y'; break; case 'Y': c = 'R'; break; case 'K': c = 'M'; break; case 'M': c = 'K'; break;
+        case 'B': c = 'V'; break; case 'V': c = 'B'; break; case 'D': c = 'H'; break; case 'H': c = 'D'; break;
+        default: break;
+        }
+    }
+    return out;
+}
+
+struct Cli {
+    std::string pair_fasta, reference, query, output, config_dir = "sample_tsa_config", alphabet = "dna-n", skip, method = "a-star-template-switch";
+    std::string rq_ranges;
+    bool no_ts = false, embedded = false, dont_extend = false;
+    long long ref_off = -1, ref_lim = -1, qry_off = -1, qry_lim = -1;
+    unsigned long long cost_limit = UINT64_MAX, memory_limit = UINT64_MAX;
+    int device = 0;
+};
+
+void usage() {
+    fprintf(stderr,
+            "Usage: tsalign-b200 align [-p PAIR_FASTA | -r REFERENCE -q QUERY] [-o OUTPUT] [-a ALPHABET] [--skip-characters S]\n"
+            "       [-c CONFIGURATION_DIRECTORY] [--no-ts] [--cost-limit N] [--memory-limit BYTES] [--rq-ranges R<a>..<b>Q<c>..<d>]\n"
+            "       [--reference-offset N] [--reference-limit N] [--query-offset N] [--query-limit N] [--use-embedded-rq-ranges]\n"
+            "       [--dont-extend-beyond-range] [--device N] (search-heuristic flags of tsalign are accepted and ignored)\n");
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 2 || std::string(argv[1]) == "-h" || std::string(argv[1]) == "--help") { usage(); return argc < 2 ? 2 : 0; }
+    const std::string sub = argv[1];
+    if (sub == "show" || sub == "preprocess") die("subcommand '" + sub + "' is not part of tsalign-b200 (alignment path only)", 2);
+    if (sub != "align") { usage(); return 2; }
+    Cli cli;
+    // flags with a value that only steer the reference's search heuristics (never the optimal cost): accepted, ignored
+    const char* ignored_with_value[] = {"-l", "--log-level", "--cache-directory", "-k", "--ts-node-ord-strategy", "--ts-min-length-strategy", "--ts-chaining-strategy",
+                                        "--ts-total-length-strategy", "--max-chaining-successors", "--max-exact-cost-function-cost", "--chaining-closed-list", "--chaining-open-list"};
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i], val;
+        bool has_inline = false;
+        size_t eq = a.find('=');
+        if (a.rfind("--", 0) == 0 && eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has_inline = true; }
+        auto value = [&]() -> std::string {
+            if (has_inline) return val;
+            if (i + 1 >= argc) die("a value is required for '" + a + "'", 2);
+            return argv[++i];
+        };
+        auto number = [&]() -> unsigned long long {
+            std::string v = value();
+            char* end = nullptr;
+            unsigned long long x = strtoull(v.c_str(), &end, 10);
+            if (v.empty() || *end) die("invalid value '" + v + "' for '" + a + "'", 2);
+            return x;
+        };
+        bool ignored = false;
+        for (const char* f : ignored_with_value) if (a == f) { value(); ignored = true; }
+        if (ignored) continue;
+        if (a == "-p" || a == "--pair-fasta") cli.pair_fasta = value();
+        else if (a == "-r" || a == "--reference") cli.reference = value();
+        else if (a == "-q" || a == "--query") cli.query = value();
+        else if (a == "-o" || a == "--output") cli.output = value();
+        else if (a == "-a" || a == "--alphabet") cli.alphabet = value();
+        else if (a == "--skip-characters") cli.skip = value();
+        else if (a == "-c" || a == "--configuration-directory") cli.config_dir = value();
+        else if (a == "--alignment-method") cli.method = value();
+        else if (a == "--ts-descendant-strategy") { if (value() != "allow-any") die("--ts-descendant-strategy allow-only-all-equal is not supported by tsalign-b200", 2); }
+        else if (a == "--no-ts") cli.no_ts = true;
+        else if (a == "--force-no-preprocessing" || a == "--force-label-correcting") {}
+        else if (a == "--cost-limit") cli.cost_limit = number();
+        else if (a == "--memory-limit") cli.memory_limit = number();
+        else if (a == "--reference-offset") cli.ref_off = (long long)number();
+        else if (a == "--reference-limit") cli.ref_lim = (long long)number();
+        else if (a == "--query-offset") cli.qry_off = (long long)number();
+        else if (a == "--query-limit") cli.qry_lim = (long long)number();
+        else if (a == "--rq-ranges") cli.rq_ranges = value();
+        else if (a == "--use-embedded-rq-ranges") cli.embedded = true;
+        else if (a == "--dont-extend-beyond-range") cli.dont_extend = true;
+        else if (a == "--device") cli.device = (int)number();
+        else die("unexpected argument '" + a + "'", 2);
+    }
+    if (cli.method != "a-star-template-switch") die("--alignment-method " + cli.method + " is not part of tsalign-b200 (only a-star-template-switch)", 2);
+    static const char* const ALPHABETS[] = {"dna", "dna-n", "rna", "rna-n", "dna-iupac", "rna-iupac"};
+    int alphabet = -1;
+    for (int k = 0; k < 6; k++) if (cli.alphabet == ALPHABETS[k]) alphabet = k;
+    if (alphabet < 0) die("invalid value '" + cli.alphabet + "' for '--alphabet'", 2);
+
+    // ---- input (align.rs:304-335) ----
+    Record ref, qry;
+    if (!cli.pair_fasta.empty()) {
+        if (!cli.reference.empty() || !cli.query.empty()) die("the argument '--pair-fasta' cannot be used with '--reference' / '--query'", 2);
+        std::vector<Record> recs = parse_fasta(cli.pair_fasta);
+        if (recs.size() != 2) die("Pair fasta file must contain exactly two records, but it contains " + std::to_string(recs.size()));
+        ref = recs[0]; qry = recs[1];
+    } else if (!cli.reference.empty() && !cli.query.empty()) {
+        std::vector<Record> a = parse_fasta(cli.reference), b = parse_fasta(cli.query);
+        if (a.size() != 1 || b.size() != 1) die("Single fasta files must contain exactly one record");
+        ref = a[0]; qry = b[0];
+    } else die("No fasta input file given");
+    if (cli.embedded && cli.skip.find('|') != std::string::npos) die("Using embedded RQ ranges, but '|' is part of the skip characters");
+    for (Record* r : {&ref, &qry}) {
+        std::string s;
+        for (char c : r->seq) if (cli.skip.find(c) == std::string::npos) s.push_back((char)toupper((unsigned char)c));
+        r->seq = s;
+    }
+    // ---- ranges (align.rs:338-379, 516-599) ----
+    long long ro = 0, rl = -1, qo = 0, ql = -1;
+    if (cli.embedded) {
+        if (!cli.rq_ranges.empty() || cli.ref_off >= 0 || cli.ref_lim >= 0 || cli.qry_off >= 0 || cli.qry_lim >= 0) die("Redundant specification of RQ ranges");
+        auto split = [&](Record& r, const char* what, long long& off, long long& lim) {
+            size_t a = r.seq.find('|');
+            if (a == std::string::npos) die(std::string("Using embedded RQ ranges, but ") + what + " sequence contains no '|' character.");
+            size_t b = r.seq.find('|', a + 1);
+            if (b == std::string::npos) die(std::string("Using embedded RQ ranges, but ") + what + " sequence contains only one '|' character.");
+            if (r.seq.find('|', b + 1) != std::string::npos) die(std::string("Using embedded RQ ranges, but ") + what + " sequence contains more than two '|' characters");
+            off = (long long)a; lim = (long long)b - 1;
+            std::string s;
+            for (char c : r.seq) if (c != '|') s.push_back(c);
+            r.seq = s;
+        };
+        split(ref, "reference", ro, rl);
+        split(qry, "query", qo, ql);
+    } else {
+        long long rr0 = 0, rr1 = (long long)ref.seq.size(), qq0 = 0, qq1 = (long long)qry.seq.size();
+        if (!cli.rq_ranges.empty()) {
+            const std::string& s = cli.rq_ranges;
+            size_t p = 0;
+            bool have_r = false, have_q = false;
+            while (p < s.size()) {
+                char which = s[p++];
+                while (p < s.size() && isspace((unsigned char)s[p])) p++;
+                size_t d0 = p; while (p < s.size() && isdigit((unsigned char)s[p])) p++;
+                std::string off = s.substr(d0, p - d0);
+                if (s.compare(p, 2, "..") != 0) die("malformed --rq-ranges '" + s + "'", 2);
+                p += 2;
+                d0 = p; while (p < s.size() && isdigit((unsigned char)s[p])) p++;
+                std::string lim = s.substr(d0, p - d0);
+                if (off.empty() || lim.empty()) die("malformed --rq-ranges '" + s + "'", 2);
+                while (p < s.size() && isspace((unsigned char)s[p])) p++;
+                if (which == 'R' && !have_r) { rr0 = atoll(off.c_str()); rr1 = atoll(lim.c_str()); have_r = true; }
+                else if (which == 'Q' && !have_q) { qq0 = atoll(off.c_str()); qq1 = atoll(lim.c_str()); have_q = true; }
+                else die("malformed --rq-ranges '" + s + "'", 2);
+            }
+            if ((have_r && (cli.ref_off >= 0 || cli.ref_lim >= 0)) || (have_q && (cli.qry_off >= 0 || cli.qry_lim >= 0))) die("Redundant specification of RQ ranges", 2);
+        }
+        ro = cli.ref_off >= 0 ? cli.ref_off : rr0; rl = cli.ref_lim >= 0 ? cli.ref_lim : rr1;
+        qo = cli.qry_off >= 0 ? cli.qry_off : qq0; ql = cli.qry_lim >= 0 ? cli.qry_lim : qq1;
+    }
+
+    // ---- cost model (util.rs:14-28) ----
+    std::string cfg_path = cli.config_dir + "/config.tsa";
+    std::ifstream cin_(cfg_path);
+    if (!cin_) die("Unable to open config file \"" + cfg_path + "\"");
+    std::stringstream cs; cs << cin_.rdbuf();
+    const std::string cfg_text = cs.str();
+    int status = 0;
+    char err[512] = {0};
+    tsa_config* cfg = tsa_config_parse(cfg_text.data(), cfg_text.size(), alphabet, &status, err, sizeof(err));
+    if (!cfg) die(std::string("cannot parse ") + cfg_path + ": " + err);
+
+    tsa_options opt;
+    memset(&opt, 0, sizeof(opt));
+    opt.no_ts = cli.no_ts; opt.device = cli.device; opt.cost_limit = cli.cost_limit; opt.memory_limit = cli.memory_limit;
+    tsa_pair pair;
+    pair.reference = ref.seq.data(); pair.reference_len = ref.seq.size();
+    pair.query = qry.seq.data(); pair.query_len = qry.seq.size();
+    pair.reference_offset = ro; pair.reference_limit = rl; pair.query_offset = qo; pair.query_limit = ql;
+    tsa_result res;
+    int rc = tsa_align_batch(cfg, &opt, &pair, 1, &res, err, sizeof(err));
+    if (rc != TSA_OK) die(std::string("alignment failed: ") + err);
+    if (res.status == TSA_ERR_INVALID_CHAR) die(std::string(strstr(res.message, "reference") ? "Reference" : "Query") + " contains non-alphabet character: " + res.message);
+    if (res.status != TSA_OK) die(std::string("alignment failed: ") + res.message);
+    if (!cli.dont_extend) fprintf(stderr, "note: tsalign-b200 does not extend the alignment beyond the given range and reports no equal-cost ranges\n");
+
+    // ---- statistics (alignment_result.rs:175-237) ----
+    const bool found = res.result_type == TSA_FOUND_TARGET;
+    const double cost = (double)res.cost;
+    const double per_base = (ref.seq.size() + qry.seq.size()) ? 2.0 * cost / (double)(ref.seq.size() + qry.seq.size()) : 0.0;
+    int ts_amount = 0;
+    for (size_t i = 0; i < res.n_ops; i++) ts_amount += res.ops[i].type == TSA_OP_TS_EXIT;
+    std::string result_line;
+    switch (res.result_type) {
+    case TSA_FOUND_TARGET: result_line = "Reached target with cost " + std::to_string(res.cost); break;
+    case TSA_EXCEEDED_COST_LIMIT: result_line = "Exceeded cost limit of " + std::to_string(res.cost); break;
+    case TSA_EXCEEDED_MEMORY_LIMIT: result_line = "Exceeded memory limit, but reached a maximum cost of " + std::to_string(res.cost); break;
+    default: result_line = "Found no target";
+    }
+    const std::string ref_name = ref.id + " " + ref.comment, qry_name = qry.id + " " + qry.comment;  // align.rs:418-419
+
+    if (!cli.output.empty()) {
+        std::ofstream out(cli.output);
+        if (!out) die("Unable to open output file \"" + cli.output + "\"");
+        out << "type = " << (found ? "\"WithTarget\"" : "\"WithoutTarget\"") << "\n";
+        if (found) {
+            out << "alignment = [";
+            for (size_t i = 0; i < res.n_ops; i++) {
+                const tsa_op& op = res.ops[i];
+                if (i) out << ", ";
+                out << "[" << op.count << ", ";
+                if (op.type == TSA_OP_TS_ENTRANCE)
+                    out << "{ TemplateSwitchEntrance = { first_offset = " << op.value << ", equal_cost_range = { min_start = 1, max_start = -1, min_end = 1, max_end = -1 }, primary = \""
+                        << (op.primary ? "Query" : "Reference") << "\", secondary = \"" << (op.secondary ? "Query" : "Reference") << "\", direction = \""
+                        << (op.direction ? "Reverse" : "Forward") << "\" } }";
+                else if (op.type == TSA_OP_TS_EXIT) out << "{ TemplateSwitchExit = { anti_primary_gap = " << op.value << " } }";
+                else out << "\"" << OP_NAMES[op.type] << "\"";
+                out << "]";
+            }
+            out << "]\n";
+        }
+        out << "reference_offset = " << ro << "\nquery_offset = " << qo << "\ncost = " << fmt_f64(cost) << "\ncost_per_base = " << fmt_f64(per_base)
+            << "\nduration_seconds = " << fmt_f64(res.duration_seconds) << "\nopened_nodes = 0.0\nclosed_nodes = 0.0\nsuboptimal_opened_nodes = 0.0"
+            << "\nsuboptimal_opened_nodes_ratio = 0.0\ntemplate_switch_amount = " << fmt_f64((double)ts_amount) << "\nruntime = 0.0\nmemory = 0.0\n\n[result]\n";
+        switch (res.result_type) {
+        case TSA_FOUND_TARGET: out << "astar_result_type = \"FoundTarget\"\ncost = " << res.cost << "\n"; break;
+        case TSA_EXCEEDED_COST_LIMIT: out << "astar_result_type = \"ExceededCostLimit\"\ncost_limit = " << res.cost << "\n"; break;
+        case TSA_EXCEEDED_MEMORY_LIMIT: out << "astar_result_type = \"ExceededMemoryLimit\"\nmax_cost = " << res.cost << "\n"; break;
+        default: out << "astar_result_type = \"NoTarget\"\n";
+        }
+        const bool rna = alphabet == TSA_ALPHABET_RNA || alphabet == TSA_ALPHABET_RNA_N || alphabet == TSA_ALPHABET_RNA_IUPAC;
+        out << "\n[sequences]\nreference_name = " << toml_string(ref_name) << "\nreference = " << toml_string(ref.seq) << "\nreference_rc = "
+            << toml_string(complement_text(ref.seq, rna)) << "\nquery_name = " << toml_string(qry_name) << "\nquery = " << toml_string(qry.seq) << "\nquery_rc = "
+            << toml_string(complement_text(qry.seq, rna)) << "\n";
+    }
+
+    if (found) printf("CIGAR: %s\n", cigar(res).c_str()); else printf("No alignment found\n");
+    printf("%s\nReference offset: %lld\nQuery offset: %lld\nCost per base: %.2f\nOpened nodes: 0\nClosed nodes: 0\nSuboptimal openend nodes: 0\n"
+           "Suboptimal openend nodes per optimal opened node: 0.00\nDuration: %.2fs\n", result_line.c_str(), ro, qo, per_base, res.duration_seconds);
+    tsa_results_free(&res, 1);
+    tsa_config_free(cfg);
+    return 0;
+}

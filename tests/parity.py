@@ -7,18 +7,37 @@ import randcfg
 import template_switch_aligner_b200 as tsa
 
 
-def check_batch(aligner, flat, pairs, no_ts=False, label=""):
-    """pairs: [(r, q) | (r, q, range)].  The product's costs must equal the scalar DP oracle's, bit for bit."""
+def check_alignment(flat, p, g, label=""):
+    """The returned alignment must rescore to the returned cost under the reference cost function
+    (compute_cost restatement, template_switch_specifics.rs:591-835) and span exactly the requested range."""
+    r, q = p[0], p[1]
+    rng = p[2] if len(p) > 2 and p[2] is not None else (0, len(r), 0, len(q))
+    assert g.ops is not None, (label, p)
+    ops = [oracle.Op(*o) for o in g.ops]
+    cost, er, eq, ok = oracle.rescore(flat, r, q, ops, rng[0], rng[2], as_searched=True)
+    assert ok and cost == g.cost and (er, eq) == (rng[1], rng[3]), (label, p, tsa.cigar_of(g.ops), cost, g.cost, er, eq)
+    assert sum(1 for o in ops if o.type == oracle.OP_TS_EXIT) == g.template_switches
+
+
+def check_batch(aligner, flat, pairs, no_ts=False, label="", expected=None):
+    """pairs: [(r, q) | (r, q, range)].  The product's costs must equal the scalar DP oracle's, bit for bit, and its
+    alignments must rescore to them.  expected: optional precomputed oracle costs (None = no target)."""
     got = aligner.align_batch(pairs)
     n_ts = 0
-    for p, g in zip(pairs, got):
+    for idx, (p, g) in enumerate(zip(pairs, got)):
         rng = p[2] if len(p) > 2 else None
-        want = oracle.dp_align(flat, p[0], p[1], rng, no_ts=no_ts)
         assert g.status == 0, (label, p, g.message)
-        assert g.result_type == want.result_type, (label, p, g.result_type, want.result_type)
-        if want.found:
-            assert g.cost == want.cost, (label, p, g.cost, want.cost, want.cigar())
+        if expected is not None:
+            want_found, want_cost = expected[idx] is not None, expected[idx]
+        else:
+            want = oracle.dp_align(flat, p[0], p[1], rng, no_ts=no_ts)
+            want_found, want_cost = want.found, want.cost
+        assert g.found == want_found, (label, p, g.result_type)
+        if want_found:
+            assert g.cost == want_cost, (label, p, g.cost, want_cost)
             n_ts += g.template_switches > 0
+            if aligner.traceback:
+                check_alignment(flat, p, g, label)
     return n_ts
 
 

@@ -11,6 +11,17 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
+def oracle_costs():
+    # tests/golden/make_oracle_costs.py: the scalar oracle's answers, computed once in the build container
+    from conftest import load_golden
+    return load_golden("oracle_costs.json")
+
+
+def _expected(oracle_costs, cfg_name, no_ts, items):
+    return [oracle_costs[f"{cfg_name}|{'nots' if no_ts else 'ts'}|{name}"] for name, _, _ in items]
+
+
+@pytest.fixture(scope="module")
 def lib():
     lib = _lib.default()
     assert lib.tsa_device_count() >= 1, "no CUDA device: the GPU tests cannot run"
@@ -24,24 +35,27 @@ def test_random_models_gpu(lib):
 
 
 @pytest.mark.parametrize("cfg_name,max_len", [("sample", 130), ("bench", 130), ("experiments", 110), ("small", 130), ("no_intra_forward_jump", 130)])
-def test_test_files_gpu(lib, configs, pairs, cfg_name, max_len):
+def test_test_files_gpu(lib, configs, pairs, oracle_costs, cfg_name, max_len):
     ocfg = parse_config_any(configs[cfg_name])
     flat = oracle.FlatConfig(ocfg)
     items = parity.test_file_pairs(pairs, ocfg.alphabet, max_len)
     assert len(items) >= 30
     for no_ts in (False, True):
         aligner = tsa.Aligner(costs=configs[cfg_name], alphabet=ocfg.alphabet, no_ts=no_ts, lib=lib)
-        parity.check_batch(aligner, flat, [(r, q) for _, r, q in items], no_ts=no_ts, label=cfg_name)
+        parity.check_batch(aligner, flat, [(r, q) for _, r, q in items], no_ts=no_ts, label=cfg_name,
+                           expected=_expected(oracle_costs, cfg_name, no_ts, items))
 
 
-def test_test_files_long_gpu(lib, configs, pairs):
-    # 200 .. 1127 bp pairs of test_files (jump kernel classes C = 9, 17, 33), sample config
+def test_test_files_long_gpu(lib, configs, pairs, oracle_costs):
+    # 200 .. 1055 bp pairs of test_files (jump kernel classes C = 9, 17, 33), sample config
     ocfg = parse_config_any(configs["sample"])
     flat = oracle.FlatConfig(ocfg)
     items = parity.test_file_pairs(pairs, ocfg.alphabet, 1055, min_len=131)
     assert len(items) >= 15
-    aligner = tsa.Aligner(costs=configs["sample"], alphabet=ocfg.alphabet, lib=lib)
-    parity.check_batch(aligner, flat, [(r, q) for _, r, q in items], label="long")
+    for no_ts in (False, True):
+        aligner = tsa.Aligner(costs=configs["sample"], alphabet=ocfg.alphabet, no_ts=no_ts, lib=lib)
+        parity.check_batch(aligner, flat, [(r, q) for _, r, q in items], no_ts=no_ts, label="long",
+                           expected=_expected(oracle_costs, "sample", no_ts, items))
 
 
 def test_reference_kats_gpu(lib, configs, kats):
@@ -49,6 +63,8 @@ def test_reference_kats_gpu(lib, configs, kats):
     aligner = tsa.Aligner(costs=configs[k["config"]], alphabet=k["alphabet"], lib=lib)
     res = aligner.align_batch([(k["reference"], k["query"], tuple(k["range"]))])[0]
     assert res.found and res.cost == k["cost"]
+    flat = oracle.FlatConfig(parse_config_any(configs[k["config"]]))
+    parity.check_alignment(flat, (k["reference"], k["query"], tuple(k["range"])), res, "tsnax")
     k = kats["match_overtakes_gap"]  # lib_tsalign/src/a_star_aligner/tests.rs:10-29
     cfg = tsa_config.rust_default(k["alphabet"])
     cfg.tables[0] = tsa_config.base_agnostic(k["alphabet"], "Primary Edit Costs", k["match"], k["substitution"], k["gap_open"], k["gap_extend"])
@@ -56,6 +72,7 @@ def test_reference_kats_gpu(lib, configs, kats):
     aligner = tsa.Aligner(costs=config_to_text(cfg), alphabet=k["alphabet"], no_ts=True, lib=lib)
     res = aligner.align_batch([(k["reference"], k["query"])])[0]
     assert res.found and res.cost == k["cost"]
+    assert tsa.cigar_of(res.ops) == k["cigar"]   # 1D2=2I: the reference's own tie-break happens to agree here
 
 
 def test_golden_toml_costs_gpu(lib, configs, toml_golden):
@@ -118,8 +135,8 @@ def test_edge_cases_gpu(lib, configs):
     res = aligner.align_batch([("ACGX", "ACGT"), ("ACGT", "ACGT", (3, 2, 0, 4)), ("ACGT", "ACGT")])
     assert [r.status for r in res] == [7, 8, 0] and res[2].cost == 0
     assert aligner.align_batch([]) == []
-    # a 3 kb pair with template switches enabled is refused loudly in this build, and runs with --no-ts
-    r, q = workloads.long_pair(0, 3000)
+    # a 1.5 kb pair with template switches enabled is refused loudly in this build, and runs with --no-ts
+    r, q = workloads.long_pair(0, 1500)
     res = aligner.align_batch([(r, q)])[0]
     assert res.status == 9
     nots = tsa.Aligner(costs=configs["sample"], no_ts=True, lib=lib)
@@ -132,7 +149,7 @@ def test_no_ts_long_gpu(lib):
     text = workloads.sample_config_text()
     flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
     nots = tsa.Aligner(costs=text, no_ts=True, lib=lib)
-    pairs = [workloads.long_pair(i, 4000) for i in range(2)]
+    pairs = [workloads.long_pair(i, 2500) for i in range(2)]
     res = nots.align_batch(pairs)
     for (r, q), g in zip(pairs, res):
         assert g.found and g.cost == oracle.dp_align(flat, r, q, no_ts=True).cost
