@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtsalign_b200.so")
+# TSA_B200_LIB: developer knob to benchmark another *CUDA build* of the same sources (e.g. different launch bounds)
+LIB_PATH = os.environ.get("TSA_B200_LIB") or os.path.join(_HERE, "libtsalign_b200.so")
 U64_MAX = (1 << 64) - 1
 
 TSA_OK = 0

@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import ctypes as C
 import pathlib
+import struct
 from dataclasses import dataclass
 from typing import Iterable, List, Optional, Sequence, Tuple, Union
 
@@ -117,31 +118,43 @@ def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_temp
     return o
 
 
-@dataclass
+_OP_STRUCT = struct.Struct("<qiiiiq")  # tsa_op: count, type, primary, secondary, direction, value
+
+
 class BatchResult:
-    """One entry of a batch: the C struct tsa_result, copied out."""
-    status: int
-    result_type: str
-    cost: int
-    template_switches: int
-    ops: Optional[List[Tuple[int, int, int, int, int, int]]]  # (count, type, primary, secondary, direction, value)
-    message: str = ""
-    duration_seconds: float = 0.0
+    """One entry of a batch: the C struct tsa_result, copied out.  `ops` (the run-length encoded alignment as
+    (count, type, primary, secondary, direction, value) tuples) is decoded on first use."""
+    __slots__ = ("status", "result_type", "cost", "template_switches", "message", "duration_seconds", "_raw", "_ops")
+
+    def __init__(self, status, result_type, cost, template_switches, raw_ops, message="", duration_seconds=0.0):
+        self.status, self.result_type, self.cost, self.template_switches = status, result_type, cost, template_switches
+        self.message, self.duration_seconds = message, duration_seconds
+        self._raw, self._ops = raw_ops, None
+
+    @property
+    def ops(self) -> Optional[List[Tuple[int, int, int, int, int, int]]]:
+        if self._ops is None and self._raw is not None:
+            self._ops = list(_OP_STRUCT.iter_unpack(self._raw))
+        return self._ops
 
     @property
     def found(self) -> bool:
         return self.status == 0 and self.result_type == "FoundTarget"
 
+    def __repr__(self):
+        return (f"BatchResult(status={self.status}, result_type={self.result_type!r}, cost={self.cost}, "
+                f"template_switches={self.template_switches}, ops={self.ops}, message={self.message!r})")
+
 
 def _copy_results(lib, res, n) -> List[BatchResult]:
     out = []
+    names = _lib.RESULT_NAMES
+    size = C.sizeof(TsaOp)
     for i in range(n):
         r = res[i]
-        ops = None
-        if r.ops:
-            ops = [(r.ops[k].count, r.ops[k].type, r.ops[k].primary, r.ops[k].secondary, r.ops[k].direction, r.ops[k].value) for k in range(r.n_ops)]
-        out.append(BatchResult(r.status, _lib.RESULT_NAMES[r.result_type], r.cost, r.template_switches, ops,
-                               r.message.decode(errors="replace"), r.duration_seconds))
+        raw = C.string_at(r.ops, r.n_ops * size) if r.ops else None
+        out.append(BatchResult(r.status, names[r.result_type], r.cost, r.template_switches, raw,
+                               r.message.decode(errors="replace") if r.status else "", r.duration_seconds))
     lib.tsa_results_free(res, n)
     return out
 

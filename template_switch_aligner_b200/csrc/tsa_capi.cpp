@@ -13,8 +13,13 @@
 
 using namespace tsa;
 
+#include <mutex>
+
+// A parsed cost model plus the engines (device buffers, stream) that tsa_align_batch reuses from call to call.
 struct tsa_config {
     HostConfig host;
+    std::mutex lock;
+    std::unique_ptr<Engine> engine[16];
 };
 
 namespace {
@@ -274,10 +279,16 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     if (!cfg || (!pairs && n) || (!out && n)) { set_err(err, errcap, "null argument"); return TSA_ERR_ARGUMENT; }
     const tsa_options o = opt ? *opt : default_options();
     auto t0 = std::chrono::steady_clock::now();
-    Engine engine(cfg->host, o.device);
+    tsa_config* mcfg = const_cast<tsa_config*>(cfg);
+    std::lock_guard<std::mutex> guard(mcfg->lock);   // one call at a time per config object (context-per-config)
+    const int slot = (o.device >= 0 && o.device < 16) ? o.device : 0;
+    if (!mcfg->engine[slot] || !mcfg->engine[slot]->ok()) mcfg->engine[slot].reset(new Engine(cfg->host, o.device));
+    Engine& engine = *mcfg->engine[slot];
     if (!engine.ok()) {
         set_err(err, errcap, engine.error());
-        return engine.error().find("CUDA") != std::string::npos ? TSA_ERR_NO_DEVICE : TSA_ERR_UNSUPPORTED;
+        const int rc = engine.error().find("CUDA") != std::string::npos ? TSA_ERR_NO_DEVICE : TSA_ERR_UNSUPPORTED;
+        mcfg->engine[slot].reset();
+        return rc;
     }
     Encoded enc;
     encode_pairs(cfg->host, pairs, n, enc);

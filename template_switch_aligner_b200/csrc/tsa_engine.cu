@@ -48,6 +48,7 @@ void launch_jump(const Chunk& ck, const int* d_list, int n_list, int max_len, in
     static bool attr_set = false;
     if (!attr_set) {
         rt::check(cudaFuncSetAttribute(k_ts_jump<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
+        rt::check(cudaFuncSetAttribute(k_ts_jump<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
         attr_set = true;
     }
 #endif

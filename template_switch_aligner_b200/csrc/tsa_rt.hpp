@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #define TSA_DEV __device__ __forceinline__
 #define TSA_KERNEL __global__
+#define TSA_LAUNCH_BOUNDS(threads, blocks) __launch_bounds__(threads, blocks)
 #define TSA_SHARED_DECL(name) extern __shared__ __align__(16) unsigned char name[]
 #define TSA_HOSTDEV __host__ __device__
 
@@ -60,6 +61,7 @@ TSA_DEV int clz_u32(uint32_t v) { return __clz((int)v); }
 #include <algorithm>
 #define TSA_DEV inline
 #define TSA_KERNEL
+#define TSA_LAUNCH_BOUNDS(threads, blocks)
 #define TSA_HOSTDEV
 #define TSA_SHARED_DECL(name) unsigned char* name = ::tsa::emu::smem()
 
