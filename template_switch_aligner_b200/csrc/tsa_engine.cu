@@ -50,6 +50,13 @@ void launch_jump(const Chunk& ck, const int* d_list, int n_list, int max_len, in
         rt::check(cudaFuncSetAttribute(k_ts_jump<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
         rt::check(cudaFuncSetAttribute(k_ts_jump<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
         attr_set = true;
+        if (getenv("TSA_B200_DEBUG")) {
+            int blocks = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_ts_jump<C>, 32 * warps, smem);
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, k_ts_jump<C>);
+            fprintf(stderr, "[tsalign_b200] k_ts_jump<%d>: %d regs, %zu B dynamic smem/block, %d blocks/SM resident\n", C, fa.numRegs, smem, blocks);
+        }
     }
 #endif
     const int n_ep = (max_len - ml + 2) / 2;
@@ -69,7 +76,7 @@ struct Engine::Impl {
     int device = 0;
     cudaStream_t stream = 0;
     std::vector<DevBuf*> dirL, DL;       // per-layer traceback codes / D matrices (traceback only)
-    DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows;
+    DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
     size_t cells = 0, ops_total = 0;
     int max_recs = 0;
@@ -270,7 +277,7 @@ void Engine::run_staged() {
     const int* d_ts_list = I.d_class_list[0];
     const unsigned ts_grid = (unsigned)((n_ts + 255) / 256);
     I.ck.round = -1;
-    if (n_ts) { TSA_LAUNCH(k_resolve, dim3(ts_grid), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts, I.opt.first_threshold); stats_.launches++; }
+    if (n_ts) { TSA_LAUNCH(k_resolve, dim3(ts_grid), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts, I.opt.first_threshold, (int*)nullptr, 0); stats_.launches++; }
     I.ck.round = 0;
     mark(0);
     fill(I.d_list_all, n_all, 0);
@@ -281,57 +288,93 @@ void Engine::run_staged() {
     }
     bool fill_pending = true;   // events 0..1 bracket a fill that has not been read yet
 
-    for (int round = 0;; round++) {
+    // Work lists per jump-kernel class, compacted on the device after every layer / round: cur[c] = the pairs of
+    // class c that are still active.  Two scratch list buffers with the layout of the class lists, swapped per step.
+    I.work_a.ensure((size_t)std::max(1, n_ts) * 4); I.work_b.ensure((size_t)std::max(1, n_ts) * 4);
+    int class_off[N_CLASS], cur_n[N_CLASS];
+    const int* cur[N_CLASS];
+    {
+        int off = 0;
+        for (int c = 0; c < N_CLASS; c++) { class_off[c] = off; off += (int)I.class_list[c].size(); }
+    }
+    for (int c = 0; c < N_CLASS; c++) { cur[c] = I.d_class_list[c]; cur_n[c] = (int)I.class_list[c].size(); }
+    int* spare[2] = {I.work_a.as<int>(), I.work_b.as<int>()};
+    int which = 0;
+    auto read_counts = [&](int* counts8) {
+        int h[16] = {0};
+        rt::d2h(h, I.counters.p, sizeof(h), I.stream);
+        rt::stream_sync(I.stream);
+        stats_.chains_run += h[1]; stats_.rows_filled += h[2]; stats_.rows_jumped += h[3]; stats_.chains_started += h[4];
+        for (int c = 0; c < N_CLASS; c++) counts8[c] = h[8 + c];
+    };
+    auto jump_class = [&](int c) {
+        long long l = 0;
+        switch (CLASS_C[c]) {
+        case 3: launch_jump<3>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+        case 5: launch_jump<5>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+        case 9: launch_jump<9>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+        case 17: launch_jump<17>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+        default: launch_jump<33>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+        }
+        stats_.launches += l; stats_.jump_launches += l;
+    };
+    bool capped = false;
+    for (int round = 0; !capped; round++) {
         I.ck.round = round;
-        if (round > 0) { mark(0); fill(d_ts_list, n_ts, 0); mark(1); fill_pending = true; }   // layer 0 again for the unresolved pairs
-        bool capped = false;
+        if (round > 0) {   // layer 0 again for the unresolved pairs
+            mark(0);
+            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) fill(cur[c], cur_n[c], 0);
+            mark(1);
+            fill_pending = true;
+        }
         for (int layer = 0;; layer++) {
             rt::dev_memset(I.counters.p, 0, 64, I.stream);
-            for (int off = 0; off < n_ts; off += 65535) {
-                const int cnt = std::min(65535, n_ts - off);
-                TSA_LAUNCH(k_clear_seeds, dim3(8, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, d_ts_list + off, cnt);
+            for (int c = 0; c < N_CLASS; c++)
+                for (int off = 0; off < cur_n[c]; off += 65535) {
+                    const int cnt = std::min(65535, cur_n[c] - off);
+                    TSA_LAUNCH(k_clear_seeds, dim3(8, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, cur[c] + off, cnt);
+                    stats_.launches++;
+                }
+            mark(2);
+            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) jump_class(c);
+            mark(3);
+            int* out = spare[which];
+            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) {
+                TSA_LAUNCH(k_advance, dim3((unsigned)((cur_n[c] + 255) / 256)), dim3(256), 0, I.stream, I.ck, cur[c], cur_n[c], out + class_off[c], 8 + c);
                 stats_.launches++;
             }
-            mark(2);
-            for (int c = 0; c < N_CLASS; c++) {
-                const int cnt = (int)I.class_list[c].size();
-                if (!cnt) continue;
-                long long l = 0;
-                switch (CLASS_C[c]) {
-                case 3: launch_jump<3>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-                case 5: launch_jump<5>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-                case 9: launch_jump<9>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-                case 17: launch_jump<17>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-                default: launch_jump<33>(I.ck, I.d_class_list[c], cnt, I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-                }
-                stats_.launches += l; stats_.jump_launches += l;
-            }
-            mark(3);
-            TSA_LAUNCH(k_advance, dim3(ts_grid), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts);
-            stats_.launches++;
-            int h_counters[8] = {0};
-            rt::d2h(h_counters, I.counters.p, sizeof(h_counters), I.stream);
-            rt::stream_sync(I.stream);
-            stats_.chains_run += h_counters[1]; stats_.rows_filled += h_counters[2]; stats_.rows_jumped += h_counters[3]; stats_.chains_started += h_counters[4];
+            int counts[N_CLASS];
+            read_counts(counts);
             if (fill_pending) { stats_.fill_ms += span(0, 1); fill_pending = false; }
             stats_.jump_ms += span(2, 3);
             stats_.layers_run = std::max(stats_.layers_run, layer + 1);
-            if (h_counters[0] == 0) break;
+            int total = 0;
+            for (int c = 0; c < N_CLASS; c++) { cur[c] = out + class_off[c]; cur_n[c] = counts[c]; total += counts[c]; }
+            which ^= 1;
+            if (total == 0) break;
             if (layer + 1 >= I.opt.max_layers) { capped = true; break; }   // fetch_staged reports the still-active pairs
             mark(0);
-            fill(d_ts_list, n_ts, layer + 1);
+            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) fill(cur[c], cur_n[c], layer + 1);
             mark(1);
             fill_pending = true;
         }
         stats_.rounds_run = round + 1;
         if (capped) break;
+        // which pairs still have to prove their optimum with a larger threshold?
         rt::dev_memset(I.counters.p, 0, 64, I.stream);
-        TSA_LAUNCH(k_resolve, dim3(ts_grid), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts, 0);
-        stats_.launches++;
-        int h_counters[8] = {0};
-        rt::d2h(h_counters, I.counters.p, sizeof(h_counters), I.stream);
-        rt::stream_sync(I.stream);
-        if (h_counters[5] == 0) break;
+        int* out = spare[which];
+        for (int c = 0; c < N_CLASS; c++) {
+            const int cnt = (int)I.class_list[c].size();
+            if (!cnt) continue;
+            TSA_LAUNCH(k_resolve, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, I.stream, I.ck, I.d_class_list[c], cnt, 0, out + class_off[c], 8 + c);
+            stats_.launches++;
+        }
+        int counts[N_CLASS];
+        read_counts(counts);
+        int total = 0;
+        for (int c = 0; c < N_CLASS; c++) { cur[c] = out + class_off[c]; cur_n[c] = counts[c]; total += counts[c]; }
+        which ^= 1;
+        if (total == 0) break;
     }
     run_trace();
 }

@@ -87,7 +87,7 @@ struct Chunk {
     int* t0;                 // [pair] target cost of layer 0 (no template switch)
     int* resolved;           // [pair] optimum proven
     int round;               // deepening round (0 = first)
-    int* counters;           // [0] pairs with next_active, [1..4] work statistics, [5] unresolved pairs
+    int* counters;           // [0] pairs with next_active, [1..4] work statistics, [8 + class] compacted list sizes
 };
 
 // ---- traceback ------------------------------------------------------------------------------------------------

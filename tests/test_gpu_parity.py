@@ -76,22 +76,28 @@ def test_reference_kats_gpu(lib, configs, kats):
 
 
 def test_golden_toml_costs_gpu(lib, configs, toml_golden):
-    # the committed result files: same sequences + recorded range -> at most the recorded cost, and equal to the oracle
+    # The committed result files of the reference (test_files/*.toml): same sequences, same range (the offsets in
+    # the file and the end point its alignment reaches) -> exactly the recorded optimal cost.
+    from helpers import ops_from_toml
+    checked = 0
     for name, g in toml_golden.items():
         p = g["parsed"]
-        if p["type"] != "WithTarget" or "no_ts" in name:
+        if p["type"] != "WithTarget":
             continue
         seqs = p["sequences"]
         ocfg = parse_config_any(configs[g["config"]])
-        try:
-            oracle.alphabets.encode(ocfg.alphabet, seqs["reference"]), oracle.alphabets.encode(ocfg.alphabet, seqs["query"])
-        except ValueError:
-            ocfg = tsa_config.parse(configs[g["config"]], "dna-n") if ocfg.alphabet == "dna-n" else ocfg
-        aligner = tsa.Aligner(costs=configs[g["config"]], alphabet=ocfg.alphabet, lib=lib)
-        res = aligner.align_batch([(seqs["reference"], seqs["query"])])[0]
+        flat = oracle.FlatConfig(ocfg)
+        cost, er, eq, ok = oracle.rescore(flat, seqs["reference"], seqs["query"], ops_from_toml(p["alignment"]), p["reference_offset"], p["query_offset"])
+        assert ok and cost == int(p["cost"])
+        rng = (p["reference_offset"], er, p["query_offset"], eq)
+        aligner = tsa.Aligner(costs=configs[g["config"]], alphabet=ocfg.alphabet, no_ts="no_ts" in name, lib=lib)
+        res = aligner.align_batch([(seqs["reference"], seqs["query"], rng)])[0]
         if res.status != 0:
-            continue  # longer than the widest jump kernel
-        assert res.found and res.cost <= int(p["cost"]), (name, res.cost, p["cost"])
+            continue  # longer than the widest jump kernel of this build
+        assert res.found and res.cost == int(p["cost"]), (name, res.cost, p["cost"])
+        parity.check_alignment(flat, (seqs["reference"], seqs["query"], rng), res, name)
+        checked += 1
+    assert checked >= 5
 
 
 def test_read_pair_batch_gpu(lib):
