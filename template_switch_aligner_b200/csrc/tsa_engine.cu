@@ -30,7 +30,7 @@ size_t jump_smem_per_warp(int A, int C) {
     while ((1 << (KL + 1)) <= LW) KL++;
     KL += 1;
     const size_t sub_bytes = ((size_t)A * LW * 2 + 15) & ~(size_t)15;
-    return sub_bytes + (size_t)KL * LW * 4;
+    return sub_bytes + (size_t)KL * LW * 4 + JUMP_GAP_BYTES;
 }
 
 int jump_warps(int A, int C) {
