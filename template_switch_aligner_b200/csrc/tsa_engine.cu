@@ -163,7 +163,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         if (I.ts_enabled) {
             if (dev_.left_flank > 0 || dev_.right_flank > 0) { I.status[i] = PAIR_ERR_FLANKS; continue; }
             int cls = -1;
-            for (int c = 0; c < N_CLASS; c++) if (W <= 32 * CLASS_C[c]) { cls = c; break; }
+            for (int c = 0; c < N_CLASS; c++) if (W <= 32 * CLASS_C[c] - 1) { cls = c; break; }   // the last column stays "infinite" (RowTable)
             if (cls < 0) { I.status[i] = PAIR_ERR_TOO_LONG; continue; }
             I.class_list[cls].push_back((int)i);
             I.class_maxlen[cls] = std::max(I.class_maxlen[cls], W - 1);
