@@ -444,6 +444,8 @@ bool flatten_config(const HostConfig& cfg, DevConfig& dev, std::vector<int>& lc_
         for (size_t i = 0; i < oc.size(); i++) kd.oc[i] = oc[i];
         kd.n_apg = (int)apg[d].size();
         for (size_t i = 0; i < apg[d].size(); i++) kd.apg[i] = apg[d][i];
+        kd.apg_nonpos = 1;
+        for (const Piece& pc : apg[d]) if (pc.hi > 0) kd.apg_nonpos = 0;
         kd.min_rest_nolc = min_cost(oc) + min_cost(ld) + min_cost(apg[d]);
         kd.min_rest = kd.min_rest_nolc + min_lc;
         dev.min_ts = std::min(dev.min_ts, kd.base + kd.min_rest);

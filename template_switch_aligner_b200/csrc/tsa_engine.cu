@@ -79,6 +79,7 @@ struct Engine::Impl {
     DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
     size_t cells = 0, ops_total = 0;
+    int max_m = 0;                       // longest query of the staged chunk (column count of the primary fill)
     int max_recs = 0;
     DevBuf cfg, lc, meta, seq, D, DT, seedA, seedB, minvec, scratch, best, best_layer, active, next_active, counters, lists, thr, ub, t0, resolved;
     std::vector<PairMeta> metas;
@@ -150,9 +151,11 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     for (auto& l : I.class_list) l.clear();
     for (auto& v : I.class_maxlen) v = 0;
     size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0;
+    I.max_m = 0;
     for (size_t i = 0; i < n; i++) {
         const PairView& pv = pairs[i];
         PairMeta& pm = I.metas[i];
+        I.max_m = std::max(I.max_m, pv.m);
         pm.n = pv.n; pm.m = pv.m; pm.ro = pv.ro; pm.rl = pv.rl; pm.qo = pv.qo; pm.ql = pv.ql;
         pm.seq_r = (long long)seq_bytes; seq_bytes += (size_t)pv.n;
         pm.seq_q = (long long)seq_bytes; seq_bytes += (size_t)pv.m;
@@ -235,6 +238,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.counters = I.counters.as<int>();
     ck.thr = I.thr.as<int>(); ck.ub = I.ub.as<int>(); ck.t0 = I.t0.as<int>(); ck.resolved = I.resolved.as<int>();
     ck.round = 0;
+    ck.kind_mask = ~0u;
     rt::stream_sync(I.stream);
     return true;
 }
@@ -268,7 +272,8 @@ void Engine::run_staged() {
             I.ck.dir = I.dirL[layer]->as<uint8_t>();
             if (I.ts_enabled) { I.DL[layer]->ensure(I.cells * 2); I.ck.D = I.DL[layer]->as<int16_t>(); }
         }
-        TSA_LAUNCH(k_primary_fill, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
+        if (I.max_m + 1 <= 32 * 5) TSA_LAUNCH(k_primary_fill<5>, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
+        else TSA_LAUNCH(k_primary_fill<K1_CB>, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
         stats_.launches++; stats_.fill_launches++;
     };
     int n_ts = 0;
@@ -318,9 +323,16 @@ void Engine::run_staged() {
         }
         stats_.launches += l; stats_.jump_launches += l;
     };
+    // Scouting round: the reverse kinds (anti-diagonal geometry, no trivial self matches) are cheap to evaluate and
+    // usually already contain the optimum.  Running them alone first gives the full rounds a tight upper bound, so
+    // that the expensive forward kinds are pruned with ub = best + 1 instead of the deepening threshold.
+    unsigned full_mask = 0, rev_mask = 0;
+    for (int k = 0; k < dev_.n_kinds; k++) { full_mask |= 1u << k; if (dev_.kinds[k].d == 1) rev_mask |= 1u << k; }
+    const bool scout = I.opt.scout_round && rev_mask != 0 && rev_mask != full_mask;
     bool capped = false;
     for (int round = 0; !capped; round++) {
         I.ck.round = round;
+        I.ck.kind_mask = (scout && round == 0) ? rev_mask : full_mask;
         if (round > 0) {   // layer 0 again for the unresolved pairs
             mark(0);
             for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) fill(cur[c], cur_n[c], 0);
@@ -360,6 +372,10 @@ void Engine::run_staged() {
         }
         stats_.rounds_run = round + 1;
         if (capped) break;
+        if (scout && round == 0) {   // nothing is proven yet: every pair goes into the first full round, same threshold
+            for (int c = 0; c < N_CLASS; c++) { cur[c] = I.d_class_list[c]; cur_n[c] = (int)I.class_list[c].size(); }
+            continue;
+        }
         // which pairs still have to prove their optimum with a larger threshold?
         rt::dev_memset(I.counters.p, 0, 64, I.stream);
         int* out = spare[which];
@@ -489,13 +505,20 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
     while (i < n) {
         size_t j = i, bytes = 0;
         while (j < n) {
-            const size_t b = (!opt.no_ts && dev_.n_kinds > 0) ? bytes_per_pair(pairs[j].n, pairs[j].m) : (size_t)(pairs[j].n + pairs[j].m) * 20 + 512;
+            const size_t cells = (size_t)(pairs[j].n + 1) * (pairs[j].m + 1);
+            size_t b = (!opt.no_ts && dev_.n_kinds > 0) ? bytes_per_pair(pairs[j].n, pairs[j].m) : (size_t)(pairs[j].n + pairs[j].m) * 20 + 512;
+            if (opt.traceback) b += cells * ((!opt.no_ts && dev_.n_kinds > 0) ? 9 : 1) + 3 * (size_t)(pairs[j].n + pairs[j].m) + 256;   // codes (+ D) of ~3 layers, ops
             if (j > i && bytes + b > opt.chunk_bytes) break;
             bytes += b; j++;
         }
         AlignOptions o = opt;
         o.chunk_bytes = std::max(opt.chunk_bytes, bytes * 2);
-        stage(pairs + i, j - i, o);
+        o.chunk_bytes = (size_t)1 << 62;   // the chunk was sized above; stage() must not refuse it
+        if (!stage(pairs + i, j - i, o)) {
+            for (size_t k = i; k < j; k++) { out[k] = PairCost(); out[k].status = PAIR_ERR_TOO_LONG; }
+            i = j;
+            continue;
+        }
         run_staged();
         fetch_staged(out + i);
         total.launches += stats_.launches; total.fill_launches += stats_.fill_launches; total.jump_launches += stats_.jump_launches;

@@ -25,6 +25,7 @@ struct KindDesc {
     int oc_lo, oc_hi, oc_skip0; // hull of the reachable first offsets; oc_skip0: offset 0 is not reachable (forward kinds)
     int n_apg;             // anti-primary-gap pieces of this direction
     Piece apg[MAX_PIECES];
+    int apg_nonpos;        // every finite anti-primary gap is <= 0: a switch never reenters right of its entrance
     int min_rest_nolc;     // min over finite (oc + ldc + apg): lower bound of everything but base, length and inner
     int min_rest;          // min_rest_nolc + cheapest finite length cost
 };
@@ -87,6 +88,7 @@ struct Chunk {
     int* t0;                 // [pair] target cost of layer 0 (no template switch)
     int* resolved;           // [pair] optimum proven
     int round;               // deepening round (0 = first)
+    unsigned kind_mask;      // kinds (index into DevConfig::kinds) evaluated by the jump kernel in this round
     int* counters;           // [0] pairs with next_active, [1..4] work statistics, [8 + class] compacted list sizes
 };
 
