@@ -173,7 +173,7 @@ def run_ours(args):
     # weak scaling: every rank aligns its own contiguous shard of the pair list
     pairs = workloads.read_pairs(batch, start=rank * batch, length=READ_LEN)
     cells = sum(len(r) * len(q) for r, q in pairs)
-    aligner = tsa.Aligner(costs=text, alphabet="dna-n", device=local, lib=lib, first_threshold=args.first_threshold, scout=not args.no_scout)
+    aligner = tsa.Aligner(costs=text, alphabet="dna-n", device=local, lib=lib, first_threshold=args.first_threshold, scout=args.scout)
 
     def barrier():
         torch.cuda.synchronize()
@@ -288,7 +288,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16384, help="pairs per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--first-threshold", type=int, default=0, help="tuning knob of the exact pruning (0 = library default)")
-    ap.add_argument("--no-scout", action="store_true", help="tuning knob: disable the reverse-kinds scouting round")
+    ap.add_argument("--scout", action="store_true", help="tuning knob: enable the reverse-kinds scouting round")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU A* for the cpu_baseline object")
     args = ap.parse_args()
     if args.impl == "reference":

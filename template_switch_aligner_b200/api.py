@@ -106,7 +106,7 @@ def _make_pairs(pairs: Sequence[tuple]):
     return arr, keep
 
 
-def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0, traceback=True, scout=True) -> TsaOptions:
+def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0, traceback=True, scout=False) -> TsaOptions:
     o = TsaOptions()
     o.no_ts = int(bool(no_ts))
     o.device = device
@@ -115,7 +115,7 @@ def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_temp
     o.max_template_switches = max_template_switches
     o.first_threshold = first_threshold
     o.no_traceback = 0 if traceback else 1
-    o.reserved = 0 if scout else 1
+    o.reserved = 1 if scout else 0
     return o
 
 
@@ -238,7 +238,7 @@ class Aligner:
     def __init__(self, *, no_ts: bool = False, min_length_strategy: str = "lookahead", chaining_strategy: str = "none",
                  total_length_strategy: str = "maximise", costs: Optional[str] = None,
                  costs_file: Optional[Union[str, pathlib.Path]] = None, alphabet: str = "dna-n", device: int = 0,
-                 first_threshold: int = 0, traceback: bool = True, scout: bool = True, lib=None) -> None:
+                 first_threshold: int = 0, traceback: bool = True, scout: bool = False, lib=None) -> None:
         if costs is not None and costs_file is not None:
             raise ValueError("Provide at most one of 'costs' or 'costs_file'.")
         if min_length_strategy not in _MIN_LENGTH:

@@ -144,7 +144,7 @@ AlignOptions engine_options(const tsa_options& o) {
     if (o.max_template_switches > 0) a.max_layers = o.max_template_switches;
     if (o.first_threshold > 0) a.first_threshold = o.first_threshold;
     a.traceback = o.no_traceback == 0;
-    a.scout_round = (o.reserved & 1) == 0;   // bit 0 of `reserved`: developer knob, disables the scouting round
+    a.scout_round = (o.reserved & 1) != 0;   // bit 0 of `reserved`: developer knob, enables the scouting round
     if (a.traceback) a.max_layers = std::min(a.max_layers, (int)MAX_TRACE_LAYERS);
     if (o.memory_limit != UINT64_MAX) a.chunk_bytes = (size_t)std::max<uint64_t>(o.memory_limit, (uint64_t)1 << 20);
     return a;

@@ -14,7 +14,7 @@ struct AlignOptions {
     bool no_ts = false;            // --no-ts: MaxTemplateSwitchCount(0), strategies/template_switch_count.rs:41-63
     int max_layers = 64;           // cap on the number of template switches per alignment
     bool traceback = true;         // produce alignments (ops), not only costs
-    bool scout_round = true;       // first round with the reverse kinds only (tightens the bound for the forward kinds)
+    bool scout_round = false;      // optional first round with the reverse kinds only; measured slower on read pairs (profiles/)
     int first_threshold = 12;      // first pruning threshold of the iterative deepening (doubles per round)
     size_t chunk_bytes = (size_t)6 << 30;  // HBM budget of one resident chunk of pairs
 };
