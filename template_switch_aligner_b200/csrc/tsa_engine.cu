@@ -61,7 +61,7 @@ void launch_jump(const Chunk& ck, const int* d_list, int n_list, int max_len, in
 #endif
     const int n_ep = (max_len - ml + 2) / 2;
     if (n_ep <= 0 || n_kinds <= 0) return;
-    const int tasks = n_kinds * JUMP_GROUPS;
+    const int tasks = n_kinds * n_ep;
     const unsigned gx = (unsigned)((tasks + warps - 1) / warps);
     for (int off = 0; off < n_list; off += 65535) {
         const int cnt = std::min(65535, n_list - off);
