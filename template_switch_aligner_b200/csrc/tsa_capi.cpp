@@ -200,7 +200,7 @@ struct tsa_batch {
 
 extern "C" {
 
-tsa_batch* tsa_batch_create(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pairs, size_t n, int* status, char* err, size_t errcap) {
+tsa_batch* tsa_batch_create(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pairs, size_t n, int* status, char* err, size_t errcap) try {
     int dummy; if (!status) status = &dummy;
     if (!cfg || (!pairs && n)) { *status = TSA_ERR_ARGUMENT; set_err(err, errcap, "null argument"); return nullptr; }
     std::unique_ptr<tsa_batch> b(new tsa_batch);
@@ -218,15 +218,22 @@ tsa_batch* tsa_batch_create(const tsa_config* cfg, const tsa_options* opt, const
     if (!b->engine->stage(b->enc.views.data(), b->enc.views.size(), ao)) { *status = TSA_ERR_UNSUPPORTED; set_err(err, errcap, "batch does not fit one chunk"); return nullptr; }
     *status = TSA_OK;
     return b.release();
+} catch (const std::exception& e) {
+    if (status) *status = TSA_ERR_INTERNAL;
+    set_err(err, errcap, e.what());
+    return nullptr;
 }
 
-int tsa_batch_run(tsa_batch* b) {
+int tsa_batch_run(tsa_batch* b) try {
     if (!b) return TSA_ERR_ARGUMENT;
     b->engine->run_staged();
     return TSA_OK;
+} catch (const std::exception& e) {
+    fprintf(stderr, "tsalign_b200: %s\n", e.what());
+    return TSA_ERR_INTERNAL;
 }
 
-int tsa_batch_fetch(tsa_batch* b, tsa_result* out) {
+int tsa_batch_fetch(tsa_batch* b, tsa_result* out) try {
     if (!b || !out) return TSA_ERR_ARGUMENT;
     b->costs.resize(b->enc.views.size());
     b->engine->fetch_staged(b->costs.data());
@@ -237,6 +244,9 @@ int tsa_batch_fetch(tsa_batch* b, tsa_result* out) {
     }
     for (size_t k = 0; k < b->enc.live.size(); k++) fill_result(out[b->enc.live[k]], b->costs[k], b->opt);
     return TSA_OK;
+} catch (const std::exception& e) {
+    fprintf(stderr, "tsalign_b200: %s\n", e.what());
+    return TSA_ERR_INTERNAL;
 }
 
 void tsa_batch_stats(const tsa_batch* b, int64_t* launches, int64_t* jump_launches, int64_t* fill_launches, int32_t* layers, int64_t* h2d_bytes, int64_t* d2h_bytes) {
@@ -276,7 +286,7 @@ int tsa_measure_addmin_peak(int device, double* s16x2_lane_ops_per_s, double* s3
 
 void tsa_batch_free(tsa_batch* b) { delete b; }
 
-int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pairs, size_t n, tsa_result* out, char* err, size_t errcap) {
+int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pairs, size_t n, tsa_result* out, char* err, size_t errcap) try {
     if (!cfg || (!pairs && n) || (!out && n)) { set_err(err, errcap, "null argument"); return TSA_ERR_ARGUMENT; }
     const tsa_options o = opt ? *opt : default_options();
     auto t0 = std::chrono::steady_clock::now();
@@ -304,6 +314,11 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     for (size_t i = 0; i < n; i++) out[i].duration_seconds = n ? secs / (double)n : 0.0;
     return TSA_OK;
+} catch (const std::exception& e) {
+    // e.g. cudaMalloc failure: drop the cached engine (its buffers) and report; nothing is thrown across the ABI
+    if (cfg) { tsa_config* mcfg = const_cast<tsa_config*>(cfg); std::lock_guard<std::mutex> guard(mcfg->lock); for (auto& en : mcfg->engine) en.reset(); }
+    set_err(err, errcap, e.what());
+    return TSA_ERR_INTERNAL;
 }
 
 void tsa_results_free(tsa_result* results, size_t n) {

@@ -21,9 +21,16 @@
 #define TSA_SHARED_DECL(name) extern __shared__ __align__(16) unsigned char name[]
 #define TSA_HOSTDEV __host__ __device__
 
+#include <stdexcept>
+#include <string>
 namespace tsa { namespace rt {
+// CUDA failures (out of memory, launch errors) surface as exceptions; the C ABI turns them into status codes.
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
 inline void check(cudaError_t e, const char* what) {
-    if (e != cudaSuccess) { fprintf(stderr, "tsalign_b200: CUDA error in %s: %s\n", what, cudaGetErrorString(e)); abort(); }
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // clear the sticky-free error state for the next call
+        throw CudaError(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+    }
 }
 } }
 #define TSA_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
