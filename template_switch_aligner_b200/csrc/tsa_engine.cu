@@ -76,7 +76,7 @@ struct Engine::Impl {
     int device = 0;
     cudaStream_t stream = 0;
     std::vector<DevBuf*> dirL, DL;       // per-layer traceback codes / D matrices (traceback only)
-    DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b;
+    DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b, tables;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
     size_t cells = 0, ops_total = 0;
     int max_m = 0;                       // longest query of the staged chunk (column count of the primary fill)
@@ -150,7 +150,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.list_all.clear();
     for (auto& l : I.class_list) l.clear();
     for (auto& v : I.class_maxlen) v = 0;
-    size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0;
+    size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0, tab = 0;
     I.max_m = 0;
     for (size_t i = 0; i < n; i++) {
         const PairView& pv = pairs[i];
@@ -162,6 +162,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         pm.vec = (long long)vec; vec += (size_t)pv.n + pv.m + 2;
         pm.scr = (long long)scr; scr += 3 * ((size_t)pv.n + 1);
         pm.mat = (long long)cells;
+        pm.tab = -1; pm.lw = 0;
         const int W = std::max(pv.n, pv.m) + 1;
         if (I.ts_enabled) {
             if (dev_.left_flank > 0 || dev_.right_flank > 0) { I.status[i] = PAIR_ERR_FLANKS; continue; }
@@ -170,6 +171,9 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
             if (cls < 0) { I.status[i] = PAIR_ERR_TOO_LONG; continue; }
             I.class_list[cls].push_back((int)i);
             I.class_maxlen[cls] = std::max(I.class_maxlen[cls], W - 1);
+            pm.lw = 32 * CLASS_C[cls];
+            pm.tab = (long long)tab;
+            tab += 4 * table_bytes(dev_.A, pm.lw);
         }
         if (I.ts_enabled || opt.traceback) cells += (size_t)(pv.n + 1) * (pv.m + 1);
         I.list_all.push_back((int)i);
@@ -195,6 +199,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     }
     I.meta.ensure(n * sizeof(PairMeta));
     I.seq.ensure(seq_bytes);
+    I.tables.ensure(tab);
     I.minvec.ensure(vec * 4);
     I.scratch.ensure(scr * 4);
     I.best.ensure(n * 4); I.best_layer.ensure(n * 4); I.active.ensure(n * 4); I.next_active.ensure(n * 4);
@@ -224,6 +229,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.seq = I.seq.as<uint8_t>();
     ck.cfg = I.cfg.as<DevConfig>();
     ck.lc = I.lc.as<int>();
+    ck.tables = I.tables.as<unsigned char>();
     ck.D = I.ts_enabled ? I.D.as<int16_t>() : nullptr;
     ck.DT = I.ts_enabled ? I.DT.as<int16_t>() : nullptr;
     ck.dir = nullptr;
@@ -292,6 +298,11 @@ void Engine::run_staged() {
         rt::stream_sync(I.stream); stats_.fill_ms += span(0, 1); run_trace(); return;
     }
     bool fill_pending = true;   // events 0..1 bracket a fill that has not been read yet
+    for (int off = 0; off < n_ts; off += 65535) {   // per-column cost tables of every (pair, secondary, direction)
+        const int cnt = std::min(65535, n_ts - off);
+        TSA_LAUNCH(k_prepare_tables, dim3(4, (unsigned)cnt), dim3(128), 0, I.stream, I.ck, d_ts_list + off, cnt);
+        stats_.launches++;
+    }
 
     // Work lists per jump-kernel class, compacted on the device after every layer / round: cur[c] = the pairs of
     // class c that are still active.  Two scratch list buffers with the layout of the class lists, swapped per step.

@@ -86,6 +86,7 @@ struct Dim { unsigned x = 1, y = 1, z = 1; Dim(unsigned a = 1, unsigned b = 1, u
 void launch(void (*entry)(void*), void* args, Dim grid, Dim block, size_t smem_bytes);
 } }
 struct tsa_emu_idx { unsigned x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };   // CUDA's 16-byte vector type
 #define threadIdx (::tsa::emu::tid())
 #define blockIdx (::tsa::emu::bid())
 #define blockDim (::tsa::emu::bdim())

@@ -56,6 +56,8 @@ struct PairMeta {
     long long mat;           // cell offset of this pair's (n+1) x (m+1) matrices in the matrix pools
     long long vec;           // int offset of this pair's row/col minima: rowmin[n+1] then colmin[m+1]
     long long scr;           // int offset of the column-tiling scratch of the primary fill: 3 * (n+1)
+    long long tab;           // byte offset of this pair's per-column cost tables (k_prepare_tables), -1 if none
+    int lw;                  // columns of one table row (32 * C of the pair's jump-kernel class)
 };
 
 // Traceback code of one cell of one layer (written by k_primary_fill, read by k_traceback).
@@ -72,6 +74,7 @@ struct Chunk {
     const uint8_t* seq;      // alphabet indices
     const DevConfig* cfg;
     const int* lc;           // dense length costs (cfg->n_lc entries)
+    unsigned char* tables;   // per pair, per (secondary, direction): sub[A][lw] u16, then open[lw], ext[lw] u32 (both halves)
     int16_t* D;              // [pair][i][j]  min_g cost of layer k at flank == L_f, clamped to INF16
     int16_t* DT;             // [pair][j][i]  the same, transposed (primary = query kinds read rows of it)
     uint8_t* dir;            // [pair][i][j]  traceback codes of the layer being filled (DIR_* bits), or null
