@@ -76,6 +76,9 @@ struct Engine::Impl {
     int device = 0;
     cudaStream_t stream = 0;
     std::vector<DevBuf*> dirL, DL;       // per-layer traceback codes / D matrices (traceback only)
+    std::vector<DevBuf*> fdL, dir2L;     // flank mode: per-layer codes of the flank planes / seed flags of plane 0
+    DevBuf PA, PB, tgt_key, best_plane;  // flank mode: ping-pong state planes, per-layer target keys
+    bool flank = false;
     DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b, tables;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
     size_t cells = 0, ops_total = 0;
@@ -127,6 +130,8 @@ Engine::Engine(const HostConfig& cfg, int device) : impl_(new Impl), host_(cfg) 
 Engine::~Engine() {
     for (DevBuf* b : impl_->dirL) delete b;
     for (DevBuf* b : impl_->DL) delete b;
+    for (DevBuf* b : impl_->fdL) delete b;
+    for (DevBuf* b : impl_->dir2L) delete b;
 #ifndef TSA_EMUL
     if (ok_) {
         cudaSetDevice(impl_->device);
@@ -145,6 +150,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.opt = opt;
     I.npairs = n;
     I.ts_enabled = !opt.no_ts && dev_.n_kinds > 0;
+    I.flank = I.ts_enabled && (dev_.left_flank > 0 || dev_.right_flank > 0);
     I.metas.assign(n, PairMeta());
     I.status.assign(n, PAIR_OK);
     I.list_all.clear();
@@ -165,7 +171,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         pm.tab = -1; pm.lw = 0;
         const int W = std::max(pv.n, pv.m) + 1;
         if (I.ts_enabled) {
-            if (dev_.left_flank > 0 || dev_.right_flank > 0) { I.status[i] = PAIR_ERR_FLANKS; continue; }
+            if (dev_.left_flank + dev_.right_flank + 1 >= KEY_PLANES) { I.status[i] = PAIR_ERR_FLANKS; continue; }
             int cls = -1;
             for (int c = 0; c < N_CLASS; c++) if (W <= 32 * CLASS_C[c] - 1) { cls = c; break; }   // the last column stays "infinite" (RowTable)
             if (cls < 0) { I.status[i] = PAIR_ERR_TOO_LONG; continue; }
@@ -206,6 +212,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.counters.ensure(64);
     I.thr.ensure(n * 4); I.ub.ensure(n * 4); I.t0.ensure(n * 4); I.resolved.ensure(n * 4);
     if (I.ts_enabled) { I.D.ensure(cells * 2); I.DT.ensure(cells * 2); I.seedA.ensure(cells * 4); I.seedB.ensure(cells * 4); }
+    if (I.flank) { I.PA.ensure(cells * 6); I.PB.ensure(cells * 6); I.tgt_key.ensure(n * 4); I.best_plane.ensure(n * 4); }
     if (opt.traceback) {
         I.ops.ensure(I.ops_total); I.ops_off.ensure(n * 8); I.ops_cap.ensure(n * 4); I.ops_len.ensure(n * 4);
         I.recs.ensure(n * (size_t)I.max_recs * sizeof(TsRecord)); I.n_recs.ensure(n * 4); I.tstatus.ensure(n * 4);
@@ -245,6 +252,10 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.thr = I.thr.as<int>(); ck.ub = I.ub.as<int>(); ck.t0 = I.t0.as<int>(); ck.resolved = I.resolved.as<int>();
     ck.round = 0;
     ck.kind_mask = ~0u;
+    ck.pl_in = nullptr; ck.pl_out = nullptr; ck.dir2 = nullptr;
+    ck.cells_total = (long long)cells;
+    ck.tgt_key = I.tgt_key.as<int>(); ck.best_plane = I.best_plane.as<int>();
+    ck.flank_mode = I.flank ? 1 : 0;
     rt::stream_sync(I.stream);
     return true;
 }
@@ -282,6 +293,60 @@ void Engine::run_staged() {
         else TSA_LAUNCH(k_primary_fill<K1_CB>, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
         stats_.launches++; stats_.fill_launches++;
     };
+    // One layer = the primary fill plus, with flank lengths > 0, the right-flank planes before it (reentry seeds ->
+    // ordinary plane) and the left-flank planes after it (ordinary plane -> template switch entrance plane).
+    auto fill_layer = [&](const int* d_list, int cnt, int layer) {
+        if (!I.flank) { fill(d_list, cnt, layer); return; }
+        const int RF = dev_.right_flank, LF = dev_.left_flank;
+        const size_t cells = I.cells;
+        uint8_t* fd = nullptr;
+        I.ck.dir2 = nullptr;
+        if (I.opt.traceback) {
+            while ((int)I.fdL.size() <= layer) { I.fdL.push_back(new DevBuf); I.dir2L.push_back(new DevBuf); }
+            I.fdL[layer]->ensure((size_t)(RF + LF) * cells);
+            I.dir2L[layer]->ensure(cells);
+            fd = I.fdL[layer]->as<uint8_t>();
+            I.ck.dir2 = I.dir2L[layer]->as<uint8_t>();
+        }
+        int16_t* A = I.PA.as<int16_t>();
+        int16_t* B = I.PB.as<int16_t>();
+        auto step = [&](const int16_t* src, int16_t* dst, int table, int plane, int final_plane, int report) {
+            for (int off = 0; off < cnt; off += 65535) {
+                const int c2 = std::min(65535, cnt - off);
+                TSA_LAUNCH(k_flank_step, dim3(16, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, src, dst,
+                           fd ? fd + (size_t)(plane - 1) * cells : (uint8_t*)nullptr, table, plane, final_plane, report, layer);
+                stats_.launches++;
+            }
+        };
+        I.ck.pl_in = nullptr;
+        if (layer > 0 && RF > 0) {
+            for (int off = 0; off < cnt; off += 65535) {
+                const int c2 = std::min(65535, cnt - off);
+                TSA_LAUNCH(k_seed_to_plane, dim3(16, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, A);
+                stats_.launches++;
+            }
+            for (int s = 1; s <= RF; s++) { step(A, B, 4, s, 0, s < RF ? 1 : 0); std::swap(A, B); }
+            I.ck.pl_in = A;
+        }
+        I.ck.pl_out = LF > 0 ? B : nullptr;
+        fill(d_list, cnt, layer);
+        if (LF > 0) {
+            // the jump kernel reads D of the entrance plane L_f: written (with its row / column minima) by the last step
+            for (int off = 0; off < cnt; off += 65535) {
+                const int c2 = std::min(65535, cnt - off);
+                TSA_LAUNCH(k_reset_minvec, dim3(4, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, layer);
+                stats_.launches++;
+            }
+            const int16_t* src = B;
+            int16_t* dst = A;
+            for (int s = 1; s <= LF; s++) {
+                step(src, dst, 3, RF + s, s == LF ? 1 : 0, 1);
+                int16_t* t = const_cast<int16_t*>(src); src = dst; dst = t;
+            }
+        }
+        TSA_LAUNCH(k_layer_finish, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, I.stream, I.ck, d_list, cnt, layer);
+        stats_.launches++;
+    };
     int n_ts = 0;
     for (int c = 0; c < N_CLASS; c++) n_ts += (int)I.class_list[c].size();
     // the TS-enabled pairs are exactly the union of the class lists, which are contiguous after list_all
@@ -290,8 +355,9 @@ void Engine::run_staged() {
     I.ck.round = -1;
     if (n_ts) { TSA_LAUNCH(k_resolve, dim3(ts_grid), dim3(256), 0, I.stream, I.ck, d_ts_list, n_ts, I.opt.first_threshold, (int*)nullptr, 0); stats_.launches++; }
     I.ck.round = 0;
+    if (I.flank) rt::dev_memset(I.tgt_key.p, 0x7f, I.npairs * 4, I.stream);
     mark(0);
-    fill(I.d_list_all, n_all, 0);
+    fill_layer(I.d_list_all, n_all, 0);
     mark(1);
     if (!I.ts_enabled || n_ts == 0) {
         rt::dev_memset(I.active.p, 0, I.npairs * 4, I.stream);   // no jump follows: nothing stays active
@@ -346,7 +412,7 @@ void Engine::run_staged() {
         I.ck.kind_mask = (scout && round == 0) ? rev_mask : full_mask;
         if (round > 0) {   // layer 0 again for the unresolved pairs
             mark(0);
-            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) fill(cur[c], cur_n[c], 0);
+            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) fill_layer(cur[c], cur_n[c], 0);
             mark(1);
             fill_pending = true;
         }
@@ -377,7 +443,7 @@ void Engine::run_staged() {
             if (total == 0) break;
             if (layer + 1 >= I.opt.max_layers) { capped = true; break; }   // fetch_staged reports the still-active pairs
             mark(0);
-            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) fill(cur[c], cur_n[c], layer + 1);
+            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) fill_layer(cur[c], cur_n[c], layer + 1);
             mark(1);
             fill_pending = true;
         }
@@ -438,6 +504,9 @@ void Engine::run_trace() {
     TraceLayers tl;
     memset(&tl, 0, sizeof(tl));
     for (size_t k = 0; k < I.dirL.size() && k <= (size_t)MAX_TRACE_LAYERS; k++) { tl.dir[k] = I.dirL[k]->as<uint8_t>(); tl.D[k] = I.DL[k]->as<int16_t>(); }
+    for (size_t k = 0; k < I.fdL.size() && k <= (size_t)MAX_TRACE_LAYERS; k++) { tl.fd[k] = I.fdL[k]->as<uint8_t>(); tl.dir2[k] = I.dir2L[k]->as<uint8_t>(); }
+    tl.cells_total = (long long)I.cells;
+    tl.rf = I.flank ? dev_.right_flank : 0; tl.lf = I.flank ? dev_.left_flank : 0;
     TraceOut to;
     memset(&to, 0, sizeof(to));
     to.ops = I.ops.as<uint8_t>(); to.ops_off = I.ops_off.as<long long>(); to.ops_cap = I.ops_cap.as<int>(); to.ops_len = I.ops_len.as<int>();

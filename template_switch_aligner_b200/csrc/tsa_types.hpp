@@ -67,6 +67,12 @@ constexpr int DIR_I_EXT = 4;      // I state extended an insertion (else: opened
 constexpr int DIR_M_SHIFT = 3;    // bits 3-4: cheapest state of the cell: 0 = N, 1 = Dl, 2 = I (ties in that order)
 constexpr int DIR_NI_IS_I = 32;   // min(N, I) is I
 constexpr int DIR_ND_IS_DL = 64;  // min(N, Dl) is Dl
+constexpr int DIR2_DL_SEED = 1;   // plane 0, flank mode: Dl state taken from the right-flank arrivals
+constexpr int DIR2_I_SEED = 2;    //                       I state taken from the right-flank arrivals
+// Flank planes: one byte per cell and plane: predecessor state (0 N, 1 Dl, 2 I, 3 none) of the N / Dl / I state in the
+// previous plane (bits 0-1 / 2-3 / 4-5) and the cheapest state of the cell (bits 6-7).
+constexpr int KEY_PLANES = 512;   // tgt_key = cost * KEY_PLANES + plane index
+constexpr int KEY_INF = 0x7f7f7f7f;   // memset-able
 
 // Everything a kernel needs about the resident chunk of pairs.
 struct Chunk {
@@ -92,6 +98,14 @@ struct Chunk {
     int* resolved;           // [pair] optimum proven
     int round;               // deepening round (0 = first)
     unsigned kind_mask;      // kinds (index into DevConfig::kinds) evaluated by the jump kernel in this round
+    // ---- flank planes (left/right flank lengths > 0); all null / 0 otherwise -------------------
+    const int16_t* pl_in;    // [state N,Dl,I][cell]: plane 0 arrivals of the right-flank run (seeds of all three gap states)
+    int16_t* pl_out;         // [state][cell]: plane 0 states, input of the left-flank run
+    uint8_t* dir2;           // [cell] plane 0: DIR2_* bits (which states were taken from pl_in)
+    long long cells_total;   // cells of the whole chunk (stride between the state planes of pl_in / pl_out)
+    int* tgt_key;            // [pair] min over the planes of this layer of (target cost * 512 + plane index)
+    int* best_plane;         // [pair] plane index (flank index + right flank length) of the best target
+    int flank_mode;          // 1: k_layer_finish does the bookkeeping of k_primary_fill's epilogue
     int* counters;           // [0] pairs with next_active, [1..4] work statistics, [8 + class] compacted list sizes
 };
 
@@ -101,6 +115,10 @@ constexpr int MAX_TRACE_LAYERS = 64;
 struct TraceLayers {
     const uint8_t* dir[MAX_TRACE_LAYERS + 1];
     const int16_t* D[MAX_TRACE_LAYERS + 1];
+    const uint8_t* dir2[MAX_TRACE_LAYERS + 1];   // flank mode: DIR2_* of plane 0
+    const uint8_t* fd[MAX_TRACE_LAYERS + 1];     // flank mode: [step 1 .. RF+LF][cell] codes of the flank planes
+    long long cells_total;
+    int rf, lf;
 };
 // One template switch of an alignment, in traceback order (last switch first).
 struct TsRecord { int kind; int first_offset; int anti_primary_gap; int length; };

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-CONFIGS = ["sample", "bench", "experiments", "small", "no_intra_forward_jump"]
+CONFIGS = ["sample", "bench", "experiments", "small", "no_intra_forward_jump", "range"]
 
 
 def work(task):
@@ -46,9 +46,15 @@ def main():
                 continue
             if cfg != "sample" and L > 560:
                 continue
+            if cfg == "range" and L > 130:
+                continue   # 11 flank planes in the scalar oracle
             tasks.append((cfg, False, name))
             tasks.append((cfg, True, name))
     out = {}
+    path = os.path.join(HERE, "oracle_costs.json")
+    if os.path.exists(path):   # incremental: keep what is already there
+        out = json.load(open(path))
+        tasks = [t for t in tasks if f"{t[0]}|{'nots' if t[1] else 'ts'}|{t[2]}" not in out]
     with mp.Pool(os.cpu_count()) as pool:
         for (cfg, no_ts, name), cost in pool.imap_unordered(work, tasks):
             if cost != "skip":

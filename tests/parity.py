@@ -9,13 +9,18 @@ import template_switch_aligner_b200 as tsa
 
 def check_alignment(flat, p, g, label=""):
     """The returned alignment must rescore to the returned cost under the reference cost function
-    (compute_cost restatement, template_switch_specifics.rs:591-835) and span exactly the requested range."""
+    (compute_cost restatement, template_switch_specifics.rs:591-835) and span exactly the requested range.
+    With flank lengths > 0 the reference's run-length encoding merges flank and non-flank operations
+    (alignment_type.rs:101-121) and its compute_cost is todo!() there: only the end points are checked (the traceback
+    kernel itself verifies that the edge costs of its path sum to the optimum, else status TSA_ERR_INTERNAL)."""
     r, q = p[0], p[1]
     rng = p[2] if len(p) > 2 and p[2] is not None else (0, len(r), 0, len(q))
     assert g.ops is not None, (label, p)
     ops = [oracle.Op(*o) for o in g.ops]
     cost, er, eq, ok = oracle.rescore(flat, r, q, ops, rng[0], rng[2], as_searched=True)
-    assert ok and cost == g.cost and (er, eq) == (rng[1], rng[3]), (label, p, tsa.cigar_of(g.ops), cost, g.cost, er, eq)
+    assert ok and (er, eq) == (rng[1], rng[3]), (label, p, tsa.cigar_of(g.ops), cost, g.cost, er, eq)
+    if flat.cfg.left_flank_length == 0 and flat.cfg.right_flank_length == 0:
+        assert cost == g.cost, (label, p, tsa.cigar_of(g.ops), cost, g.cost)
     assert sum(1 for o in ops if o.type == oracle.OP_TS_EXIT) == g.template_switches
 
 
@@ -56,12 +61,12 @@ def test_file_pairs(pairs, alphabet, max_len, min_len=0):
     return out
 
 
-def random_model_batches(lib, seeds, max_len, pairs_per_model=6, device=0, first_threshold=0):
+def random_model_batches(lib, seeds, max_len, pairs_per_model=6, device=0, first_threshold=0, flanks=False):
     """Random cost models (pieces, quirks, infinite entries) x random pairs and ranges."""
     total_ts = 0
     for seed in seeds:
         rng = random.Random(seed)
-        cfg = randcfg.random_config(rng, flanks=False)
+        cfg = randcfg.random_config(rng, flanks=flanks)
         flat = oracle.FlatConfig(cfg)
         ps = []
         for _ in range(pairs_per_model):

@@ -14,6 +14,22 @@ def test_random_models_emulated():
     assert n_ts > 10
 
 
+def test_random_models_with_flanks_emulated():
+    # left / right flank lengths 0..2: flank planes, three-state seeds of the ordinary plane, plane-aware traceback
+    n_ts = parity.random_model_batches(emul(), range(1000, 1040), max_len=12, flanks=True)
+    assert n_ts > 5
+
+
+def test_range_config_emulated(configs, pairs):
+    # test_files/config/range: flank lengths 5 / 5 (the only shipped config with flanks)
+    ocfg = parse_config_any(configs["range"])
+    assert (ocfg.left_flank_length, ocfg.right_flank_length) == (5, 5)
+    flat = oracle.FlatConfig(ocfg)
+    items = parity.test_file_pairs(pairs, ocfg.alphabet, 24)
+    aligner = tsa.Aligner(costs=configs["range"], alphabet=ocfg.alphabet, lib=emul())
+    parity.check_batch(aligner, flat, [(r, q) for _, r, q in items], label="range")
+
+
 @pytest.mark.parametrize("cfg_name,max_len", [("sample", 45), ("bench", 40), ("small", 40)])
 def test_test_files_emulated(configs, pairs, cfg_name, max_len):
     ocfg = parse_config_any(configs[cfg_name])

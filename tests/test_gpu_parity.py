@@ -34,6 +34,28 @@ def test_random_models_gpu(lib):
     assert n_ts > 30
 
 
+def test_random_models_with_flanks_gpu(lib):
+    n_ts = parity.random_model_batches(lib, range(1000, 1100), max_len=20, pairs_per_model=8, flanks=True)
+    assert n_ts > 20
+
+
+def test_flank_config_gpu(lib, configs, pairs, oracle_costs):
+    # test_files/config/range (flank lengths 5 / 5) on the test files; BASELINE config 3 shape (1 kb, flanks 50) at 2 pairs
+    ocfg = parse_config_any(configs["range"])
+    flat = oracle.FlatConfig(ocfg)
+    items = parity.test_file_pairs(pairs, ocfg.alphabet, 130)
+    aligner = tsa.Aligner(costs=configs["range"], alphabet=ocfg.alphabet, lib=lib)
+    parity.check_batch(aligner, flat, [(r, q) for _, r, q in items], label="range", expected=_expected(oracle_costs, "range", False, items))
+    text = workloads.sample_config_text().replace("left_flank_length = 0", "left_flank_length = 50").replace("right_flank_length = 0", "right_flank_length = 50")
+    big = [workloads.long_pair(i, 1000, n_tsm=5) for i in range(2)]
+    a = tsa.Aligner(costs=text, lib=lib)
+    b = tsa.Aligner(costs=workloads.sample_config_text(), lib=lib)
+    ra, rb = a.align_batch(big), b.align_batch(big)
+    for x, y in zip(ra, rb):
+        assert x.status == 0 and x.found and y.found and x.ops is not None
+        assert x.cost >= y.cost    # sample flank tables cost at least the primary table: flanks can only add cost
+
+
 @pytest.mark.parametrize("cfg_name,max_len", [("sample", 130), ("bench", 130), ("experiments", 110), ("small", 130), ("no_intra_forward_jump", 130)])
 def test_test_files_gpu(lib, configs, pairs, oracle_costs, cfg_name, max_len):
     ocfg = parse_config_any(configs[cfg_name])
