@@ -104,7 +104,13 @@ void assemble_ops(tsa_result& r, const PairCost& pc) {
             out.push_back(op);
             continue;
         }
-        if (!out.empty() && out.back().type == (int32_t)u) { out.back().count++; continue; }
+        // alignment_type.rs:101-121: flank and non-flank variants of the same primary operation repeat each other; a
+        // merged run carries the label of its last operation (a_star_aligner.rs:100-122 walks the path backwards)
+        if (!out.empty()) {
+            const int32_t pt = out.back().type;
+            const bool same = pt == (int32_t)u || (pt < 8 && u < 8 && (pt & 3) == (u & 3));
+            if (same) { out.back().count++; out.back().type = u; continue; }
+        }
         tsa_op op;
         memset(&op, 0, sizeof(op));
         op.type = u; op.count = 1;
@@ -133,7 +139,7 @@ void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
     case PAIR_ERR_TOO_LONG: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "template switches need sequences of at most 1055 characters in this build"); break;
     case PAIR_ERR_COST_RANGE: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "alignment cost exceeds the 16-bit lanes of the template-switch kernel"); break;
     case PAIR_ERR_LAYER_CAP: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "more template switches than max_template_switches still improve the cost"); break;
-    case PAIR_ERR_FLANKS: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "flank lengths > 0 with template switches are not built yet"); break;
+    case PAIR_ERR_FLANKS: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "flank lengths above 255 are not supported"); break;
     default: r.status = TSA_ERR_ARGUMENT; break;
     }
 }
