@@ -6,7 +6,8 @@ switch, default `tsalign align` cost model (sample_tsa_config), batched per GPU.
 
 One "step" = one pass of the hot path (layer loop: primary fill + TS jump kernels) over one batch of pairs that is
 already resident in HBM.  `value` = GCUPS (sum |R||Q| over all ranks' pairs / max-over-ranks time / 1e9), `e2e` = the
-same metric through the public call `Aligner.align_batch` with host buffers (encode + H2D + kernels + D2H per step).
+same metric through the C ABI call `tsa_align_batch` with host buffers (encode + H2D + kernels + D2H + result assembly
+per step).
 Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference's A* (oracle/, the
 reference is Rust and cannot be built in this image) on the host cores for the same workload.
 """
@@ -219,15 +220,38 @@ def run_ours(args):
         raise SystemExit(f"bench.py: {len(bad)} pairs did not produce an alignment cost: {bad[0]}")
 
     # ---- end-to-end arm: public API with host buffers, every step ------------------------------------------
-    aligner.align_batch(pairs[: min(256, batch)])  # warm the allocator
+    # The timed call is the C ABI entry `tsa_align_batch` (include/tsalign_b200.h) on host buffers: an array of tsa_pair
+    # pointing at the ASCII sequences in host memory in, an array of tsa_result (costs + run-length encoded alignments
+    # in host memory) out.  Encoding, H2D, all kernels, D2H and result assembly are inside the call; building the
+    # ctypes view of the inputs and turning the results into Python objects (the Python mirror's job) are outside.
+    import ctypes as C
+    from template_switch_aligner_b200 import api
+    arr, keep = api._make_pairs(pairs)
+    opt = api._options(False, local, None, None, first_threshold=args.first_threshold, traceback=True, scout=args.scout)
+    err = C.create_string_buffer(512)
+
+    def abi_call():
+        res = (_lib.TsaResult * max(1, batch))()
+        rc = lib.tsa_align_batch(aligner.config._h, C.byref(opt), arr, batch, res, err, len(err))
+        if rc != 0:
+            raise SystemExit(f"bench.py: tsa_align_batch failed: {err.value!r}")
+        return res
+
+    lib.tsa_results_free(abi_call(), batch)  # warm the allocator (device buffers of the engine are sized once)
     barrier()
     t1 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(e2e_steps):
-        e2e_res = aligner.align_batch(pairs)
+    for step in range(e2e_steps):
+        res = abi_call()
+        if step + 1 < e2e_steps:
+            lib.tsa_results_free(res, batch)
     barrier()
     e2e_elapsed = max_over_ranks(time.perf_counter() - t1)
-    assert experiment or [r.cost for r in e2e_res] == [r.cost for r in results]
+    e2e_costs = [res[i].cost for i in range(batch)]
+    e2e_ops = sum(res[i].n_ops for i in range(batch))
+    lib.tsa_results_free(res, batch)
+    del keep
+    assert experiment or (e2e_costs == [r.cost for r in results] and e2e_ops == sum(len(r.ops) for r in results))
 
     if rank != 0:
         if world > 1:

@@ -309,8 +309,10 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     }
     Encoded enc;
     encode_pairs(cfg->host, pairs, n, enc);
+    auto t1 = std::chrono::steady_clock::now();
     std::vector<PairCost> costs(enc.views.size());
     engine.align_costs(enc.views.data(), enc.views.size(), engine_options(o), costs.data());
+    auto t2 = std::chrono::steady_clock::now();
     for (size_t i = 0; i < n; i++) {
         memset(&out[i], 0, sizeof(tsa_result));
         out[i].status = enc.pair_status[i];
@@ -318,6 +320,10 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     }
     for (size_t k = 0; k < enc.live.size(); k++) fill_result(out[enc.live[k]], costs[k], o);
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (getenv("TSA_B200_DEBUG"))
+        fprintf(stderr, "[tsalign_b200] align_batch n=%zu: encode %.2f ms, engine %.2f ms, results %.2f ms\n", n,
+                1e3 * std::chrono::duration<double>(t1 - t0).count(), 1e3 * std::chrono::duration<double>(t2 - t1).count(),
+                1e3 * (secs - std::chrono::duration<double>(t2 - t0).count()));
     for (size_t i = 0; i < n; i++) out[i].duration_seconds = n ? secs / (double)n : 0.0;
     return TSA_OK;
 } catch (const std::exception& e) {

@@ -3,6 +3,7 @@
 #include "tsa_engine.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "tsa_kernels.cuh"
@@ -80,6 +81,8 @@ struct Engine::Impl {
     DevBuf PA, PB, tgt_key, best_plane;  // flank mode: ping-pong state planes, per-layer target keys
     bool flank = false;
     DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b, tables;
+    DevBuf wave_prefix, wave_progress, wave_ticket;   // k_affine_wave: first ticket per pair, progress flag per strip, ticket counter
+    int wave_tickets = 0;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
     size_t cells = 0, ops_total = 0;
     int max_m = 0;                       // longest query of the staged chunk (column count of the primary fill)
@@ -181,8 +184,22 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
             pm.tab = (long long)tab;
             tab += 4 * table_bytes(dev_.A, pm.lw);
         }
-        if (I.ts_enabled || opt.traceback) cells += (size_t)(pv.n + 1) * (pv.m + 1);
+        if (I.ts_enabled) cells += (size_t)(pv.n + 1) * (pv.m + 1);
+        else if (opt.traceback) cells += (size_t)(pv.rl - pv.ro + 1) * (size_t)wave_dir_stride(pv.ql - pv.qo + 1);   // k_affine_wave: codes of the range, padded rows
         I.list_all.push_back((int)i);
+    }
+    if (!I.ts_enabled) {
+        std::vector<int> prefix(I.list_all.size() + 1, 0);
+        for (size_t k = 0; k < I.list_all.size(); k++) {
+            const PairView& pv = pairs[I.list_all[k]];
+            prefix[k + 1] = prefix[k] + wave_strips(pv.ql - pv.qo + 1);
+        }
+        I.wave_tickets = prefix.back();
+        I.wave_prefix.ensure(prefix.size() * 4);
+        I.wave_progress.ensure((size_t)std::max(1, I.wave_tickets) * 4);
+        I.wave_ticket.ensure(4);
+        rt::h2d(I.wave_prefix.p, prefix.data(), prefix.size() * 4, I.stream);
+        rt::stream_sync(I.stream);   // `prefix` is a local
     }
     I.cells = cells;
     I.max_recs = std::min(opt.max_layers, MAX_TRACE_LAYERS);
@@ -274,6 +291,7 @@ void Engine::run_staged() {
     const size_t k1_smem = (size_t)K1_WARPS * MAX_ALPHABET * MAX_ALPHABET * sizeof(int);
     rt::dev_memset(I.active.p, 0, I.npairs * 4, I.stream);
     rt::dev_memset(I.next_active.p, 0, I.npairs * 4, I.stream);
+    if (!I.ts_enabled) { run_wave(); run_trace(); return; }
 #ifndef TSA_EMUL
     auto mark = [&](int k) { rt::check(cudaEventRecord(I.ev[k], I.stream), "cudaEventRecord"); };
     auto span = [&](int a, int b) { float ms = 0; rt::check(cudaEventSynchronize(I.ev[b]), "cudaEventSynchronize"); cudaEventElapsedTime(&ms, I.ev[a], I.ev[b]); return (double)ms; };
@@ -472,6 +490,53 @@ void Engine::run_staged() {
     run_trace();
 }
 
+// --no-ts: one launch of the wavefront kernel over all strips of all pairs (tsa_wave.cuh).
+void Engine::run_wave() {
+    Impl& I = *impl_;
+    const int n_all = (int)I.list_all.size();
+    if (n_all == 0 || I.wave_tickets == 0) return;
+    if (I.opt.traceback) {
+        while (I.dirL.empty()) { I.dirL.push_back(new DevBuf); I.DL.push_back(new DevBuf); }
+        I.dirL[0]->ensure(I.cells);
+        I.ck.dir = I.dirL[0]->as<uint8_t>();
+    } else I.ck.dir = nullptr;
+    rt::dev_memset(I.wave_progress.p, 0, (size_t)I.wave_tickets * 4, I.stream);
+    rt::dev_memset(I.wave_ticket.p, 0, 4, I.stream);
+    WaveArgs wa;
+    wa.list = I.d_list_all; wa.n_list = n_all; wa.strip_prefix = I.wave_prefix.as<int>();
+    wa.progress = I.wave_progress.as<int>(); wa.ticket = I.wave_ticket.as<int>();
+    const size_t smem = (size_t)WAVE_SMEM_INTS * sizeof(int);
+    int blocks = (I.wave_tickets + WAVE_WARPS - 1) / WAVE_WARPS;
+#ifndef TSA_EMUL
+    static int resident = 0;
+    if (!resident) {
+        cudaDeviceProp prop;
+        rt::check(cudaGetDeviceProperties(&prop, I.device), "cudaGetDeviceProperties");
+        int per_sm = 0;
+        rt::check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_affine_wave<true>, 32 * WAVE_WARPS, smem), "occupancy");
+        resident = std::max(1, per_sm) * prop.multiProcessorCount;
+        if (getenv("TSA_B200_DEBUG")) {
+            cudaFuncAttributes fa, fb;
+            cudaFuncGetAttributes(&fa, k_affine_wave<true>); cudaFuncGetAttributes(&fb, k_affine_wave<false>);
+            fprintf(stderr, "[tsalign_b200] k_affine_wave: %d / %d regs (trace / costs), %d blocks/SM resident\n", fa.numRegs, fb.numRegs, per_sm);
+        }
+    }
+    blocks = std::min(blocks, resident);   // persistent: every warp takes strips from the ticket until none is left
+    rt::check(cudaEventRecord(I.ev[0], I.stream), "cudaEventRecord");
+#else
+    blocks = std::min(blocks, 2);
+#endif
+    if (I.opt.traceback) TSA_LAUNCH(k_affine_wave<true>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), smem, I.stream, I.ck, wa);
+    else TSA_LAUNCH(k_affine_wave<false>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), smem, I.stream, I.ck, wa);
+    stats_.launches++; stats_.fill_launches++;
+#ifndef TSA_EMUL
+    rt::check(cudaEventRecord(I.ev[1], I.stream), "cudaEventRecord");
+    rt::check(cudaEventSynchronize(I.ev[1]), "cudaEventSynchronize");
+    float ms = 0; cudaEventElapsedTime(&ms, I.ev[0], I.ev[1]);
+    stats_.fill_ms += ms;
+#endif
+}
+
 template <int C>
 static void launch_trace(const Chunk& ck, const TraceLayers& tl, TraceOut to, DevBuf& rows, const int* d_list, int n_list, int rows_max, int A,
                          cudaStream_t stream, long long& launches) {
@@ -507,6 +572,7 @@ void Engine::run_trace() {
     for (size_t k = 0; k < I.fdL.size() && k <= (size_t)MAX_TRACE_LAYERS; k++) { tl.fd[k] = I.fdL[k]->as<uint8_t>(); tl.dir2[k] = I.dir2L[k]->as<uint8_t>(); }
     tl.cells_total = (long long)I.cells;
     tl.rf = I.flank ? dev_.right_flank : 0; tl.lf = I.flank ? dev_.left_flank : 0;
+    tl.wave = I.ts_enabled ? 0 : 1;
     TraceOut to;
     memset(&to, 0, sizeof(to));
     to.ops = I.ops.as<uint8_t>(); to.ops_off = I.ops_off.as<long long>(); to.ops_cap = I.ops_cap.as<int>(); to.ops_len = I.ops_len.as<int>();
@@ -582,25 +648,42 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
     // Greedy chunking in input order under the HBM budget.
     size_t i = 0;
     EngineStats total;
+    size_t budget = opt.chunk_bytes;
+    if (budget == 0) {
+#ifndef TSA_EMUL
+        size_t free_b = 0, total_b = 0;
+        rt::check(cudaSetDevice(impl_->device), "cudaSetDevice");
+        rt::check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
+        budget = std::max<size_t>((size_t)1 << 30, free_b / 2);
+#else
+        budget = (size_t)1 << 30;
+#endif
+    }
     while (i < n) {
         size_t j = i, bytes = 0;
         while (j < n) {
             const size_t cells = (size_t)(pairs[j].n + 1) * (pairs[j].m + 1);
             size_t b = (!opt.no_ts && dev_.n_kinds > 0) ? bytes_per_pair(pairs[j].n, pairs[j].m) : (size_t)(pairs[j].n + pairs[j].m) * 20 + 512;
             if (opt.traceback) b += cells * ((!opt.no_ts && dev_.n_kinds > 0) ? 9 : 1) + 3 * (size_t)(pairs[j].n + pairs[j].m) + 256;   // codes (+ D) of ~3 layers, ops
-            if (j > i && bytes + b > opt.chunk_bytes) break;
+            if (j > i && bytes + b > budget) break;
             bytes += b; j++;
         }
+        const auto cs = std::chrono::steady_clock::now();
         AlignOptions o = opt;
-        o.chunk_bytes = std::max(opt.chunk_bytes, bytes * 2);
         o.chunk_bytes = (size_t)1 << 62;   // the chunk was sized above; stage() must not refuse it
         if (!stage(pairs + i, j - i, o)) {
             for (size_t k = i; k < j; k++) { out[k] = PairCost(); out[k].status = PAIR_ERR_TOO_LONG; }
             i = j;
             continue;
         }
+        const auto c0 = std::chrono::steady_clock::now();
         run_staged();
+        const auto c1 = std::chrono::steady_clock::now();
         fetch_staged(out + i);
+        if (getenv("TSA_B200_DEBUG"))
+            fprintf(stderr, "[tsalign_b200] chunk of %zu pairs: stage %.2f ms, run %.2f ms, fetch %.2f ms\n", j - i,
+                    1e3 * std::chrono::duration<double>(c0 - cs).count(), 1e3 * std::chrono::duration<double>(c1 - c0).count(),
+                    1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - c1).count());
         total.launches += stats_.launches; total.fill_launches += stats_.fill_launches; total.jump_launches += stats_.jump_launches;
         total.layers_run = std::max(total.layers_run, stats_.layers_run);
         total.h2d_bytes += stats_.h2d_bytes; total.d2h_bytes += stats_.d2h_bytes;

@@ -16,7 +16,7 @@ struct AlignOptions {
     bool traceback = true;         // produce alignments (ops), not only costs
     bool scout_round = false;      // optional first round with the reverse kinds only; measured slower on read pairs (profiles/)
     int first_threshold = 12;      // first pruning threshold of the iterative deepening (doubles per round)
-    size_t chunk_bytes = (size_t)6 << 30;  // HBM budget of one resident chunk of pairs
+    size_t chunk_bytes = 0;        // HBM budget of one resident chunk of pairs; 0 = half of the free device memory
 };
 
 // One pair, already encoded as alphabet indices.
@@ -74,6 +74,7 @@ public:
     void run_staged();
     void fetch_staged(PairCost* out);
     void run_trace();
+    void run_wave();
 
     const EngineStats& stats() const { return stats_; }
     static size_t bytes_per_pair(int n, int m);

@@ -61,6 +61,11 @@ TSA_DEV int atomic_min_s32(int* p, int v) { return atomicMin(p, v); }
 TSA_DEV int atomic_or_s32(int* p, int v) { return atomicOr(p, v); }
 TSA_DEV int atomic_add_s32(int* p, int v) { return atomicAdd(p, v); }
 TSA_DEV int clz_u32(uint32_t v) { return __clz((int)v); }
+// producer / consumer flags between warps of one launch (k_affine_wave): release store, acquire load, L2 data load
+TSA_DEV int ld_acquire_s32(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+TSA_DEV void st_release_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+TSA_DEV int ld_cg_s32(const int* p) { return __ldcg(p); }
+TSA_DEV void spin_pause() { __nanosleep(40); }
 }  // namespace tsa
 
 #else
@@ -80,6 +85,7 @@ Fiber* cur();
 unsigned char* smem();
 void warp_barrier();
 void block_barrier();
+void spin_yield();
 uint32_t* warp_slots();
 uint3e tid(); uint3e bid(); uint3e bdim(); uint3e gdim();
 struct Dim { unsigned x = 1, y = 1, z = 1; Dim(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
@@ -155,8 +161,17 @@ inline int atomic_min_s32(int* p, int v) { int o = *p; if (v < o) *p = v; return
 inline int atomic_or_s32(int* p, int v) { int o = *p; *p = o | v; return o; }
 inline int atomic_add_s32(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline int clz_u32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+inline int ld_acquire_s32(const int* p) { return *(const volatile int*)p; }
+inline void st_release_s32(int* p, int v) { *(volatile int*)p = v; }
+inline int ld_cg_s32(const int* p) { return *(const volatile int*)p; }
+inline void spin_pause() { emu::spin_yield(); }   // lets the other warps of the block run
 }  // namespace tsa
 #endif
+
+namespace tsa {
+TSA_DEV int imin(int a, int b) { return a < b ? a : b; }
+TSA_DEV int imax(int a, int b) { return a > b ? a : b; }
+}  // namespace tsa
 
 // ---------------------------------------------------------------------------- device memory (both builds)
 namespace tsa { namespace rt {

@@ -119,6 +119,7 @@ struct TraceLayers {
     const uint8_t* fd[MAX_TRACE_LAYERS + 1];     // flank mode: [step 1 .. RF+LF][cell] codes of the flank planes
     long long cells_total;
     int rf, lf;
+    int wave;                                    // codes written by k_affine_wave: alignment range only, rows padded to 8 bytes
 };
 // One template switch of an alignment, in traceback order (last switch first).
 struct TsRecord { int kind; int first_offset; int anti_primary_gap; int length; };

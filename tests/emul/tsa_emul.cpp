@@ -77,6 +77,7 @@ static void wait_on(Barrier& b) {
     else while (b.gen == gen) yield();
 }
 void warp_barrier() { wait_on(g_warp_bar[g_cur->warp]); }
+void spin_yield() { yield(); }   // a polling loop: no progress of its own, the deadlock check still sees the others
 void block_barrier() { wait_on(g_block_bar); }
 
 static void fiber_main() {

@@ -74,3 +74,23 @@ def test_python_surface_emulated(configs):
         tsa.Aligner(costs="x", costs_file="y", lib=emul())
     with pytest.raises(ValueError):
         tsa.Aligner(min_length_strategy="bogus", lib=emul())
+
+
+def test_no_ts_multi_strip_emulated(configs):
+    # k_affine_wave: pairs wider than one 256-column strip (boundary column + progress flags between warps), with
+    # ranges that do not start at a strip boundary, ragged lengths, and a batch that mixes one- and many-strip pairs
+    from template_switch_aligner_b200 import workloads
+    ocfg = parse_config_any(configs["sample"])
+    flat = oracle.FlatConfig(ocfg)
+    cases = []
+    for idx, length in enumerate((255, 256, 257, 300, 520, 700)):
+        r, q = workloads.long_pair(idx, length, sub_rate=0.03, indel_rate=0.02)
+        cases.append((r, q))
+    r, q = workloads.long_pair(7, 600, sub_rate=0.02, indel_rate=0.01)
+    cases.append((r, q, (13, len(r) - 5, 40, len(q))))
+    cases.append((r[:40], q, (0, 40, 0, len(q))))          # short reference, three strips of query
+    cases.append((r, q[:33]))
+    cases.append(("ACGT", "ACGA"))
+    for tb in (True, False):
+        aligner = tsa.Aligner(costs=configs["sample"], no_ts=True, traceback=tb, lib=emul())
+        parity.check_batch(aligner, flat, cases, no_ts=True, label="wave")

@@ -173,11 +173,19 @@ def test_edge_cases_gpu(lib, configs):
 
 
 def test_no_ts_long_gpu(lib):
-    # BASELINE config 4 shape (10 kb, --no-ts) at 2 pairs: column-tiled primary fill
+    # BASELINE config 4 shape (--no-ts, long pairs): k_affine_wave with many strips per pair and many pairs in flight
+    # (strips of one pair on different SMs, boundary columns through L2), ragged lengths, ranges; alignments rescored
     text = workloads.sample_config_text()
     flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+    pairs = [workloads.long_pair(i, 700 + 37 * i, sub_rate=0.02, indel_rate=0.01) for i in range(48)]
+    pairs += [workloads.long_pair(100 + i, 2500) for i in range(3)]
+    r, q = workloads.long_pair(200, 3000)
+    pairs.append((r, q, (100, len(r) - 7, 321, len(q) - 1)))
+    expected = [oracle.dp_align(flat, p[0], p[1], p[2] if len(p) > 2 else None, no_ts=True).cost for p in pairs]
+    for tb in (True, False):
+        nots = tsa.Aligner(costs=text, no_ts=True, traceback=tb, lib=lib)
+        parity.check_batch(nots, flat, pairs, no_ts=True, label="wave", expected=expected)
+    # one 10 kb pair (40 strips): cost against the oracle, alignment rescored
+    r, q = workloads.long_pair(0, 10000)
     nots = tsa.Aligner(costs=text, no_ts=True, lib=lib)
-    pairs = [workloads.long_pair(i, 2500) for i in range(2)]
-    res = nots.align_batch(pairs)
-    for (r, q), g in zip(pairs, res):
-        assert g.found and g.cost == oracle.dp_align(flat, r, q, no_ts=True).cost
+    parity.check_batch(nots, flat, [(r, q)], no_ts=True, label="wave10k")
