@@ -106,6 +106,10 @@ def default():
     """The product library.  Raises if it has not been built -- there is nothing to fall back to."""
     global _DEFAULT
     if _DEFAULT is None:
+        alt = os.environ.get("TSALIGN_B200_LIB")   # developer knob: an alternative build of the same CUDA library
+        if alt:
+            _DEFAULT = bind(C.CDLL(alt))
+            return _DEFAULT
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()' "

@@ -106,7 +106,7 @@ def _make_pairs(pairs: Sequence[tuple]):
     return arr, keep
 
 
-def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0, traceback=True, scout=False) -> TsaOptions:
+def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0, traceback=True, scout=False, dev_flags=0) -> TsaOptions:
     o = TsaOptions()
     o.no_ts = int(bool(no_ts))
     o.device = device
@@ -115,7 +115,7 @@ def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_temp
     o.max_template_switches = max_template_switches
     o.first_threshold = first_threshold
     o.no_traceback = 0 if traceback else 1
-    o.reserved = 1 if scout else 0
+    o.reserved = (1 if scout else 0) | (dev_flags & ~1)   # developer knobs of the engine (tsa_capi.cpp: engine_options)
     return o
 
 
@@ -238,7 +238,7 @@ class Aligner:
     def __init__(self, *, no_ts: bool = False, min_length_strategy: str = "lookahead", chaining_strategy: str = "none",
                  total_length_strategy: str = "maximise", costs: Optional[str] = None,
                  costs_file: Optional[Union[str, pathlib.Path]] = None, alphabet: str = "dna-n", device: int = 0,
-                 first_threshold: int = 0, traceback: bool = True, scout: bool = False, lib=None) -> None:
+                 first_threshold: int = 0, traceback: bool = True, scout: bool = False, dev_flags: int = 0, lib=None) -> None:
         if costs is not None and costs_file is not None:
             raise ValueError("Provide at most one of 'costs' or 'costs_file'.")
         if min_length_strategy not in _MIN_LENGTH:
@@ -254,6 +254,7 @@ class Aligner:
         self.device = device
         self.traceback = bool(traceback)        # False: optimal costs only
         self.scout = bool(scout)                # tuning of the exact pruning only
+        self.dev_flags = int(dev_flags)         # developer knobs (2: no column windows for medium pairs; 4: small windows, emulator only)
         self.first_threshold = first_threshold  # tuning of the exact pruning only; results do not depend on it
         self.config = Config(costs, alphabet, lib=self._lib)
 
@@ -263,7 +264,7 @@ class Aligner:
         arr, keep = _make_pairs(pairs)
         res = (TsaResult * max(1, len(pairs)))()
         err = C.create_string_buffer(512)
-        opt = _options(self.no_ts, self.device, cost_limit, memory_limit, first_threshold=self.first_threshold, traceback=self.traceback, scout=self.scout)
+        opt = _options(self.no_ts, self.device, cost_limit, memory_limit, first_threshold=self.first_threshold, traceback=self.traceback, scout=self.scout, dev_flags=self.dev_flags)
         rc = self._lib.tsa_align_batch(self.config._h, C.byref(opt), arr, len(pairs), res, err, len(err))
         if rc != 0:
             raise TsaError(rc, err.value.decode(errors="replace"))
@@ -291,7 +292,7 @@ class Aligner:
 
 def align(reference: object, query: object, **kwargs: object) -> Optional[Alignment]:
     """One-call convenience wrapper (mirror of tsalign.align)."""
-    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib", "first_threshold", "traceback", "scout")}
+    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib", "first_threshold", "traceback", "scout", "dev_flags")}
     align_kwargs = {k: v for k, v in kwargs.items() if k not in aligner_kwargs}
     return Aligner(**aligner_kwargs).align(reference, query, **align_kwargs)
 
@@ -306,7 +307,7 @@ class StagedBatch:
         arr, keep = _make_pairs(pairs)
         status = C.c_int(0)
         err = C.create_string_buffer(512)
-        opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit, first_threshold=aligner.first_threshold, traceback=aligner.traceback, scout=aligner.scout)
+        opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit, first_threshold=aligner.first_threshold, traceback=aligner.traceback, scout=aligner.scout, dev_flags=aligner.dev_flags)
         self._h = self._lib.tsa_batch_create(aligner.config._h, C.byref(opt), arr, self.n, C.byref(status), err, len(err))
         if not self._h:
             raise TsaError(status.value, err.value.decode(errors="replace"))

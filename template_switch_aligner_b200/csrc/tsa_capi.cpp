@@ -136,7 +136,7 @@ void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
         }
         break;
     case PAIR_NO_TARGET: r.status = TSA_OK; r.result_type = TSA_NO_TARGET; break;
-    case PAIR_ERR_TOO_LONG: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "template switches need sequences of at most 1055 characters in this build"); break;
+    case PAIR_ERR_TOO_LONG: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "template-switch column windows exceed 1056 columns at this cost threshold"); break;
     case PAIR_ERR_COST_RANGE: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "alignment cost exceeds the 16-bit lanes of the template-switch kernel"); break;
     case PAIR_ERR_LAYER_CAP: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "more template switches than max_template_switches still improve the cost"); break;
     case PAIR_ERR_FLANKS: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "flank lengths above 255 are not supported"); break;
@@ -151,6 +151,8 @@ AlignOptions engine_options(const tsa_options& o) {
     if (o.first_threshold > 0) a.first_threshold = o.first_threshold;
     a.traceback = o.no_traceback == 0;
     a.scout_round = (o.reserved & 1) != 0;   // bit 0 of `reserved`: developer knob, enables the scouting round
+    a.no_windows = (o.reserved & 2) != 0;    // bit 1: developer knob, medium pairs skip the column-window stage
+    a.test_small_windows = (o.reserved & 4) != 0;   // bit 2: honoured by emulator builds only
     if (a.traceback) a.max_layers = std::min(a.max_layers, (int)MAX_TRACE_LAYERS);
     if (o.memory_limit != UINT64_MAX) a.chunk_bytes = (size_t)std::max<uint64_t>(o.memory_limit, (uint64_t)1 << 20);
     return a;

@@ -396,6 +396,8 @@ bool flatten_config(const HostConfig& cfg, DevConfig& dev, std::vector<int>& lc_
         return false;
     dev.n_ld = (int)ld.size();
     for (size_t i = 0; i < ld.size(); i++) dev.ld[i] = ld[i];
+    dev.ld_lo = INT32_MAX; dev.ld_hi = INT32_MIN;
+    for (const Piece& pc : ld) { dev.ld_lo = std::min(dev.ld_lo, pc.lo); dev.ld_hi = std::max(dev.ld_hi, pc.hi); }
     const bool exit_possible = cfg.evaluate(3, 0) < (uint64_t)INF32;  // exit needs ldc(0) finite (context.rs:622-633)
 
     dev.n_kinds = 0;
@@ -446,6 +448,10 @@ bool flatten_config(const HostConfig& cfg, DevConfig& dev, std::vector<int>& lc_
         for (size_t i = 0; i < apg[d].size(); i++) kd.apg[i] = apg[d][i];
         kd.apg_nonpos = 1;
         for (const Piece& pc : apg[d]) if (pc.hi > 0) kd.apg_nonpos = 0;
+        kd.apg_lo = INT32_MAX; kd.apg_hi = INT32_MIN;
+        for (const Piece& pc : apg[d]) { kd.apg_lo = std::min(kd.apg_lo, pc.lo); kd.apg_hi = std::max(kd.apg_hi, pc.hi); }
+        kd.min_ext = INF32;
+        for (int x = 0; x < A; x++) kd.min_ext = std::min(kd.min_ext, dev.ext[kd.table][x]);
         kd.min_rest_nolc = min_cost(oc) + min_cost(ld) + min_cost(apg[d]);
         kd.min_rest = kd.min_rest_nolc + min_lc;
         dev.min_ts = std::min(dev.min_ts, kd.base + kd.min_rest);

@@ -12,8 +12,12 @@ namespace tsa {
 
 namespace {
 
-constexpr int N_CLASS = 5;
-const int CLASS_C[N_CLASS] = {3, 5, 9, 17, 33};   // columns per lane of k_ts_jump<C>: 96 .. 1056 columns
+// Jump-kernel classes by pair width.  0..3: k_ts_jump<C, false> over the whole sequences (96 .. 544 columns).
+// 4 ("medium", up to 1055): column windows of 544 columns first (k_ts_jump<17, true>), whole sequences with C = 33 for
+// the pairs whose windows did not fit.  5 ("long", anything wider): windows of 544, then windows of 1056 columns; a pair
+// whose windows do not fit those either is refused (PAIR_ERR_TOO_LONG).
+constexpr int N_CLASS = 6;
+const int CLASS_C[N_CLASS] = {3, 5, 9, 17, 33, 33};
 
 struct DevBuf {
     void* p = nullptr;
@@ -41,22 +45,23 @@ int jump_warps(int A, int C) {
     return w;
 }
 
-template <int C>
-void launch_jump(const Chunk& ck, const int* d_list, int n_list, int max_len, int A, int n_kinds, int ml, cudaStream_t stream, long long& launches) {
+template <int C, bool WIN>
+void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len, int A, int n_kinds, int ml, cudaStream_t stream, long long& launches) {
+    ck.win_stage = stage;
     const int warps = jump_warps(A, C);
     const size_t smem = jump_smem_per_warp(A, C) * warps;
 #ifndef TSA_EMUL
     static bool attr_set = false;
     if (!attr_set) {
-        rt::check(cudaFuncSetAttribute(k_ts_jump<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
-        rt::check(cudaFuncSetAttribute(k_ts_jump<C>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
+        rt::check(cudaFuncSetAttribute(k_ts_jump<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
+        rt::check(cudaFuncSetAttribute(k_ts_jump<C, WIN>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
         attr_set = true;
         if (getenv("TSA_B200_DEBUG")) {
             int blocks = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_ts_jump<C>, 32 * warps, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_ts_jump<C, WIN>, 32 * warps, smem);
             cudaFuncAttributes fa;
-            cudaFuncGetAttributes(&fa, k_ts_jump<C>);
-            fprintf(stderr, "[tsalign_b200] k_ts_jump<%d>: %d regs, %zu B dynamic smem/block, %d blocks/SM resident\n", C, fa.numRegs, smem, blocks);
+            cudaFuncGetAttributes(&fa, k_ts_jump<C, WIN>);
+            fprintf(stderr, "[tsalign_b200] k_ts_jump<%d,%d>: %d regs, %zu B dynamic smem/block, %d blocks/SM resident\n", C, (int)WIN, fa.numRegs, smem, blocks);
         }
     }
 #endif
@@ -66,7 +71,8 @@ void launch_jump(const Chunk& ck, const int* d_list, int n_list, int max_len, in
     const unsigned gx = (unsigned)((tasks + warps - 1) / warps);
     for (int off = 0; off < n_list; off += 65535) {
         const int cnt = std::min(65535, n_list - off);
-        TSA_LAUNCH(k_ts_jump<C>, dim3(gx, (unsigned)cnt), dim3(32 * warps), smem, stream, ck, d_list + off, cnt);
+        auto kern = k_ts_jump<C, WIN>;
+        TSA_LAUNCH(kern, dim3(gx, (unsigned)cnt), dim3(32 * warps), smem, stream, ck, d_list + off, cnt);
         launches++;
     }
 }
@@ -81,6 +87,9 @@ struct Engine::Impl {
     DevBuf PA, PB, tgt_key, best_plane;  // flank mode: ping-pong state planes, per-layer target keys
     bool flank = false;
     DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b, tables;
+    DevBuf band, winflag;                             // column windows: band vectors of the fill, overflow flags
+    bool any_win = false;
+    std::vector<int> h_winflag;
     DevBuf wave_prefix, wave_progress, wave_ticket;   // k_affine_wave: first ticket per pair, progress flag per strip, ticket counter
     int wave_tickets = 0;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
@@ -157,6 +166,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.metas.assign(n, PairMeta());
     I.status.assign(n, PAIR_OK);
     I.list_all.clear();
+    I.any_win = false;
     for (auto& l : I.class_list) l.clear();
     for (auto& v : I.class_maxlen) v = 0;
     size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0, tab = 0;
@@ -175,12 +185,16 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         const int W = std::max(pv.n, pv.m) + 1;
         if (I.ts_enabled) {
             if (dev_.left_flank + dev_.right_flank + 1 >= KEY_PLANES) { I.status[i] = PAIR_ERR_FLANKS; continue; }
-            int cls = -1;
-            for (int c = 0; c < N_CLASS; c++) if (W <= 32 * CLASS_C[c] - 1) { cls = c; break; }   // the last column stays "infinite" (RowTable)
-            if (cls < 0) { I.status[i] = PAIR_ERR_TOO_LONG; continue; }
+            int cls = N_CLASS - 1;
+            for (int c = 0; c + 1 < N_CLASS; c++) if (W <= 32 * CLASS_C[c] - 1) { cls = c; break; }   // the last column stays "infinite" (RowTable)
+#ifdef TSA_EMUL
+            if (opt.test_small_windows && W > 48) cls = N_CLASS - 1;
+#endif
             I.class_list[cls].push_back((int)i);
             I.class_maxlen[cls] = std::max(I.class_maxlen[cls], W - 1);
-            pm.lw = 32 * CLASS_C[cls];
+            pm.lw = cls == N_CLASS - 1 ? (W + 7) & ~7 : 32 * CLASS_C[cls];
+            pm.win = (cls == 4 && !opt.no_windows) || cls == 5 ? 1 : 0;
+            if (pm.win) I.any_win = true;
             pm.tab = (long long)tab;
             tab += 4 * table_bytes(dev_.A, pm.lw);
         }
@@ -229,6 +243,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.counters.ensure(64);
     I.thr.ensure(n * 4); I.ub.ensure(n * 4); I.t0.ensure(n * 4); I.resolved.ensure(n * 4);
     if (I.ts_enabled) { I.D.ensure(cells * 2); I.DT.ensure(cells * 2); I.seedA.ensure(cells * 4); I.seedB.ensure(cells * 4); }
+    if (I.any_win) { I.band.ensure(vec * 8); I.winflag.ensure(n * 4); }
     if (I.flank) { I.PA.ensure(cells * 6); I.PB.ensure(cells * 6); I.tgt_key.ensure(n * 4); I.best_plane.ensure(n * 4); }
     if (opt.traceback) {
         I.ops.ensure(I.ops_total); I.ops_off.ensure(n * 8); I.ops_cap.ensure(n * 4); I.ops_len.ensure(n * 4);
@@ -273,6 +288,9 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.cells_total = (long long)cells;
     ck.tgt_key = I.tgt_key.as<int>(); ck.best_plane = I.best_plane.as<int>();
     ck.flank_mode = I.flank ? 1 : 0;
+    ck.band = I.any_win ? I.band.as<int>() : nullptr;
+    ck.winflag = I.any_win ? I.winflag.as<int>() : nullptr;
+    ck.win_stage = 0;
     rt::stream_sync(I.stream);
     return true;
 }
@@ -292,6 +310,7 @@ void Engine::run_staged() {
     rt::dev_memset(I.active.p, 0, I.npairs * 4, I.stream);
     rt::dev_memset(I.next_active.p, 0, I.npairs * 4, I.stream);
     if (!I.ts_enabled) { run_wave(); run_trace(); return; }
+    if (I.any_win) rt::dev_memset(I.winflag.p, 0, I.npairs * 4, I.stream);
 #ifndef TSA_EMUL
     auto mark = [&](int k) { rt::check(cudaEventRecord(I.ev[k], I.stream), "cudaEventRecord"); };
     auto span = [&](int a, int b) { float ms = 0; rt::check(cudaEventSynchronize(I.ev[b]), "cudaEventSynchronize"); cudaEventElapsedTime(&ms, I.ev[a], I.ev[b]); return (double)ms; };
@@ -409,12 +428,28 @@ void Engine::run_staged() {
     };
     auto jump_class = [&](int c) {
         long long l = 0;
-        switch (CLASS_C[c]) {
-        case 3: launch_jump<3>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-        case 5: launch_jump<5>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-        case 9: launch_jump<9>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-        case 17: launch_jump<17>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
-        default: launch_jump<33>(I.ck, cur[c], cur_n[c], I.class_maxlen[c], dev_.A, dev_.n_kinds, dev_.ml, I.stream, l); break;
+        const int ml_ = dev_.ml, A_ = dev_.A, nk = dev_.n_kinds, mx = I.class_maxlen[c];
+        switch (c) {
+        case 0: launch_jump<3, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break;
+        case 1: launch_jump<5, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break;
+        case 2: launch_jump<9, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break;
+        case 3: launch_jump<17, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break;
+        case 4:   // medium: windows of 544 columns, then the whole sequences for the pairs that were flagged
+            if (I.opt.no_windows) { launch_jump<33, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break; }
+            launch_jump<17, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            launch_jump<33, false>(I.ck, 2, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            break;
+        default:  // long: windows of 544, then of 1056 columns
+#ifdef TSA_EMUL
+            if (I.opt.test_small_windows) {
+                launch_jump<3, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+                launch_jump<5, true>(I.ck, 2, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+                break;
+            }
+#endif
+            launch_jump<17, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            launch_jump<33, true>(I.ck, 2, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            break;
         }
         stats_.launches += l; stats_.jump_launches += l;
     };
@@ -537,7 +572,7 @@ void Engine::run_wave() {
 #endif
 }
 
-template <int C>
+template <int C, bool WIN>
 static void launch_trace(const Chunk& ck, const TraceLayers& tl, TraceOut to, DevBuf& rows, const int* d_list, int n_list, int rows_max, int A,
                          cudaStream_t stream, long long& launches) {
     if (n_list <= 0) return;
@@ -546,7 +581,7 @@ static void launch_trace(const Chunk& ck, const TraceLayers& tl, TraceOut to, De
 #ifndef TSA_EMUL
     static bool attr_set = false;
     if (!attr_set) {
-        rt::check(cudaFuncSetAttribute(k_traceback<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
+        rt::check(cudaFuncSetAttribute(k_traceback<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
         attr_set = true;
     }
 #endif
@@ -558,7 +593,8 @@ static void launch_trace(const Chunk& ck, const TraceLayers& tl, TraceOut to, De
     to.rows_stride = stride;
     for (int off = 0; off < n_list; off += slice) {
         const int cnt = std::min(slice, n_list - off);
-        TSA_LAUNCH(k_traceback<C>, dim3((unsigned)((cnt + warps - 1) / warps)), dim3(32 * warps), smem, stream, ck, tl, to, d_list + off, cnt);
+        auto kern = k_traceback<C, WIN>;
+        TSA_LAUNCH(kern, dim3((unsigned)((cnt + warps - 1) / warps)), dim3(32 * warps), smem, stream, ck, tl, to, d_list + off, cnt);
         launches++;
     }
 }
@@ -579,18 +615,23 @@ void Engine::run_trace() {
     to.recs = I.recs.as<TsRecord>(); to.max_recs = I.max_recs; to.n_recs = I.n_recs.as<int>(); to.status = I.tstatus.as<int>();
     long long l = 0;
     if (!I.ts_enabled) {
-        launch_trace<3>(I.ck, tl, to, I.rows, I.d_list_all, (int)I.list_all.size(), 0, dev_.A, I.stream, l);
+        launch_trace<3, false>(I.ck, tl, to, I.rows, I.d_list_all, (int)I.list_all.size(), 0, dev_.A, I.stream, l);
     } else {
         for (int c = 0; c < N_CLASS; c++) {
             const int cnt = (int)I.class_list[c].size();
             if (!cnt) continue;
             const int rows_max = std::min(dev_.lmax, I.class_maxlen[c]);
-            switch (CLASS_C[c]) {
-            case 3: launch_trace<3>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
-            case 5: launch_trace<5>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
-            case 9: launch_trace<9>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
-            case 17: launch_trace<17>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
-            default: launch_trace<33>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            switch (c) {
+            case 0: launch_trace<3, false>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            case 1: launch_trace<5, false>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            case 2: launch_trace<9, false>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            case 3: launch_trace<17, false>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            case 4: launch_trace<33, false>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
+            default:
+#ifdef TSA_EMUL
+                if (I.opt.test_small_windows) { launch_trace<5, true>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break; }
+#endif
+                launch_trace<33, true>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
             }
         }
     }
@@ -605,6 +646,8 @@ void Engine::fetch_staged(PairCost* out) {
     rt::d2h(I.h_best.data(), I.best.p, n * 4, I.stream);
     rt::d2h(I.h_layer.data(), I.best_layer.p, n * 4, I.stream);
     rt::d2h(I.h_active.data(), I.active.p, n * 4, I.stream);
+    I.h_winflag.assign(n, 0);
+    if (I.any_win && I.ts_enabled) rt::d2h(I.h_winflag.data(), I.winflag.p, n * 4, I.stream);
     rt::stream_sync(I.stream);
     stats_.d2h_bytes = (long long)(n * 12);
     for (size_t i = 0; i < n; i++) {
@@ -612,6 +655,7 @@ void Engine::fetch_staged(PairCost* out) {
         pc = PairCost();
         pc.status = I.status[i];
         if (pc.status != PAIR_OK) continue;
+        if (I.h_winflag[i] & 2) { pc.status = PAIR_ERR_TOO_LONG; continue; }   // a column window did not fit the widest class
         if (I.h_best[i] >= INF32) { pc.status = PAIR_NO_TARGET; continue; }
         // The jump kernel computes in saturating s16: every path cheaper than INF16 is exact, so a result below
         // INF16 is the optimum; above it a cheaper template-switch path may have been saturated away.

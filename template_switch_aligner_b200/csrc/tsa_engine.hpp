@@ -16,6 +16,8 @@ struct AlignOptions {
     bool traceback = true;         // produce alignments (ops), not only costs
     bool scout_round = false;      // optional first round with the reverse kinds only; measured slower on read pairs (profiles/)
     int first_threshold = 12;      // first pruning threshold of the iterative deepening (doubles per round)
+    bool no_windows = false;       // developer knob: pairs of 545..1055 characters skip the column-window stage (parity tests)
+    bool test_small_windows = false;  // emulator builds only: pairs wider than 48 use 96 / 160-column windows (CPU tests of the window logic)
     size_t chunk_bytes = 0;        // HBM budget of one resident chunk of pairs; 0 = half of the free device memory
 };
 

@@ -59,6 +59,8 @@ TSA_DEV uint32_t min_s16x2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 TSA_DEV uint32_t add_s16x2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 TSA_DEV int atomic_min_s32(int* p, int v) { return atomicMin(p, v); }
 TSA_DEV int atomic_or_s32(int* p, int v) { return atomicOr(p, v); }
+TSA_DEV int atomic_max_s32(int* p, int v) { return atomicMax(p, v); }
+TSA_DEV int atomic_and_s32(int* p, int v) { return atomicAnd(p, v); }
 TSA_DEV int atomic_add_s32(int* p, int v) { return atomicAdd(p, v); }
 TSA_DEV int clz_u32(uint32_t v) { return __clz((int)v); }
 // producer / consumer flags between warps of one launch (k_affine_wave): release store, acquire load, L2 data load
@@ -159,6 +161,8 @@ inline uint32_t min_s16x2(uint32_t a, uint32_t b) { return pack16(std::min<int>(
 inline uint32_t add_s16x2(uint32_t a, uint32_t b) { return pack16((int16_t)(lo16(a) + lo16(b)), (int16_t)(hi16(a) + hi16(b))); }
 inline int atomic_min_s32(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 inline int atomic_or_s32(int* p, int v) { int o = *p; *p = o | v; return o; }
+inline int atomic_max_s32(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
+inline int atomic_and_s32(int* p, int v) { int o = *p; *p = o & v; return o; }
 inline int atomic_add_s32(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline int clz_u32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 inline int ld_acquire_s32(const int* p) { return *(const volatile int*)p; }

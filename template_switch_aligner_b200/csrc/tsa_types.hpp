@@ -28,6 +28,8 @@ struct KindDesc {
     int apg_nonpos;        // every finite anti-primary gap is <= 0: a switch never reenters right of its entrance
     int min_rest_nolc;     // min over finite (oc + ldc + apg): lower bound of everything but base, length and inner
     int min_rest;          // min_rest_nolc + cheapest finite length cost
+    int min_ext;           // cheapest gap-extend cost of this kind's secondary edit table (column windows: bounds deletion runs)
+    int apg_lo, apg_hi;    // hull of the finite anti-primary-gap pieces
 };
 
 // Flattened TemplateSwitchConfig (config.rs:24-49) in device memory.
@@ -44,6 +46,7 @@ struct DevConfig {
     int lc_tail;
     int n_ld;
     Piece ld[MAX_PIECES];                    // LengthDifference pieces
+    int ld_lo, ld_hi;                        // their hull
     int n_kinds;
     KindDesc kinds[MAX_KINDS];
     int min_ts;                              // lower bound on the cost of any template switch
@@ -57,7 +60,8 @@ struct PairMeta {
     long long vec;           // int offset of this pair's row/col minima: rowmin[n+1] then colmin[m+1]
     long long scr;           // int offset of the column-tiling scratch of the primary fill: 3 * (n+1)
     long long tab;           // byte offset of this pair's per-column cost tables (k_prepare_tables), -1 if none
-    int lw;                  // columns of one table row (32 * C of the pair's jump-kernel class)
+    int lw;                  // columns of one table row (32 * C of the pair's jump-kernel class; windowed pairs: the whole row, padded to 8)
+    int win;                 // 1: the jump / traceback kernels run on column windows of this pair (k_ts_jump<C, true>)
 };
 
 // Traceback code of one cell of one layer (written by k_primary_fill, read by k_traceback).
@@ -106,6 +110,12 @@ struct Chunk {
     int* tgt_key;            // [pair] min over the planes of this layer of (target cost * 512 + plane index)
     int* best_plane;         // [pair] plane index (flank index + right flank length) of the best target
     int flank_mode;          // 1: k_layer_finish does the bookkeeping of k_primary_fill's epilogue
+    // ---- column windows (pairs wider than a non-windowed jump class, see k_ts_jump) ------------------------------
+    int* band;               // per pair at 2 * vec: rowlo[n+1], rowhi[n+1], collo[m+1], colhi[m+1]: first / last anti coordinate with
+                             // D < thr - min_ts (the only cells a template switch below the threshold can start from); null: unused
+    int* winflag;            // [pair] bit 0: a chain's window did not fit the first-stage class in this layer (redo in the second
+                             // stage); bit 1: it did not fit the widest class either (the pair is refused)
+    int win_stage;           // 0: not a windowed launch; 1: first stage; 2: second stage (only pairs with bit 0 set)
     int* counters;           // [0] pairs with next_active, [1..4] work statistics, [8 + class] compacted list sizes
 };
 

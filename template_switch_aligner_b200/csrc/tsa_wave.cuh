@@ -21,6 +21,9 @@
 
 namespace tsa {
 
+#ifndef TSA_WAVE_BLOCKS_PER_SM
+#define TSA_WAVE_BLOCKS_PER_SM 5
+#endif
 constexpr int WAVE_CB = 8;                 // columns per lane
 constexpr int WAVE_SW = 32 * WAVE_CB;      // columns per strip
 constexpr int WAVE_WARPS = 4;
@@ -40,24 +43,24 @@ struct WaveArgs {
 };
 
 template <bool TRACE>
-TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, 4) k_affine_wave(Chunk ck, WaveArgs wa) {
+TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_affine_wave(Chunk ck, WaveArgs wa) {
     TSA_SHARED_DECL(smem_raw);
     constexpr int CB = WAVE_CB;
     const int lane = lane_id();
-    int* subP = reinterpret_cast<int*>(smem_raw);                 // [r][q], column MAX_ALPHABET - 1 = "no character"
+    // substitution costs [r][q] with row stride A + 1 (dense: the 25 entries of a 5-letter alphabet sit in 25 different
+    // banks); column A = "no character" (infinite).  Then the gap costs by character.
+    const DevConfig* cfg = ck.cfg;
+    const int A = cfg->A, ws = A + 1;
+    int* subP = reinterpret_cast<int*>(smem_raw);
     int* openP = subP + MAX_ALPHABET * MAX_ALPHABET;
     int* extP = openP + MAX_ALPHABET;
-    const DevConfig* cfg = ck.cfg;
-    {
-        const int A = cfg->A;
-        for (int t = (int)threadIdx.x; t < MAX_ALPHABET * MAX_ALPHABET; t += (int)blockDim.x) {
-            const int r = t / MAX_ALPHABET, q = t % MAX_ALPHABET;
-            subP[t] = (r < A && q < A) ? imin(cfg->sub[0][t], INF32) : INF32;
-        }
-        for (int t = (int)threadIdx.x; t < MAX_ALPHABET; t += (int)blockDim.x) {
-            openP[t] = t < A ? imin(cfg->open[0][t], INF32) : INF32;
-            extP[t] = t < A ? imin(cfg->ext[0][t], INF32) : INF32;
-        }
+    for (int t = (int)threadIdx.x; t < A * ws; t += (int)blockDim.x) {
+        const int r = t / ws, q = t % ws;
+        subP[t] = q < A ? imin(cfg->sub[0][r * MAX_ALPHABET + q], INF32) : INF32;
+    }
+    for (int t = (int)threadIdx.x; t < MAX_ALPHABET; t += (int)blockDim.x) {
+        openP[t] = t < A ? imin(cfg->open[0][t], INF32) : INF32;
+        extP[t] = t < A ? imin(cfg->ext[0][t], INF32) : INF32;
     }
     sync_block();
     const int total = wa.strip_prefix[wa.n_list];
@@ -85,10 +88,11 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, 4) k_affine_wave(Chunk ck, Wa
         for (int c = 0; c < CB; c++) {
             const int j = j0 + c;
             const bool has = j >= 1 && j <= mm;
-            const int qc = has ? (int)Q[j - 1] : MAX_ALPHABET - 1;
+            const int qc = has ? (int)Q[j - 1] : A;
             qoff[c] = qc;
             opQ[c] = has ? openP[qc] : INF32;
             exQ[c] = has ? extP[qc] : INF32;
+            (void)0;
             Mup[c] = INF32; Dlup[c] = INF32; NIup[c] = INF32;
         }
         int diag_in = INF32;                 // M(i - 1, j0 - 1)
@@ -120,7 +124,7 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, 4) k_affine_wave(Chunk ck, Wa
             if (i >= 0 && i <= nn) {
                 const int opR = i > 0 ? openP[rch] : INF32;
                 const int exR = i > 0 ? extP[rch] : INF32;
-                const int* srow = subP + rch * MAX_ALPHABET;
+                const int* srow = subP + rch * ws;
                 int prevM = i > 0 ? diag_in : INF32;
                 int left_nd = lnd, left_i = li;
                 uint32_t w0 = 0, w1 = 0;
@@ -146,7 +150,6 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, 4) k_affine_wave(Chunk ck, Wa
                     }
                     Mup[c] = M; Dlup[c] = dl; NIup[c] = imin(nn_, iv);
                     left_nd = nd; left_i = iv;
-                    if (i == nn && c == tcol) tgt = M;                                  // target: any gap state (context.rs:731-748)
                 }
                 diag_in = imin(lnd, li);
                 out_nd = left_nd; out_i = left_i; out_r = rch;
@@ -158,6 +161,9 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, 4) k_affine_wave(Chunk ck, Wa
             }
         }
         if (last_strip) {
+            // every lane's Mup holds row nn now; target: any gap state (context.rs:731-748)
+#pragma unroll
+            for (int c = 0; c < CB; c++) if (c == tcol) tgt = Mup[c];
             tgt = reduce_min_s32(tgt);
             if (lane == 0) { ck.best[b] = tgt; ck.best_layer[b] = 0; ck.active[b] = 0; }
         }

@@ -94,3 +94,40 @@ def test_no_ts_multi_strip_emulated(configs):
     for tb in (True, False):
         aligner = tsa.Aligner(costs=configs["sample"], no_ts=True, traceback=tb, lib=emul())
         parity.check_batch(aligner, flat, cases, no_ts=True, label="wave")
+
+
+def _narrow_model(text, off, ld, lmax):
+    """The sample cost model with small offset / length-difference / length hulls, so that column windows fit 96 columns."""
+    text = text.replace("RQQROffset\n -inf -100 101", f"RQQROffset\n -inf -{off} {off + 1}").replace("RRQQOffset\n -inf -100 101", f"RRQQOffset\n -inf -{off} {off + 1}")
+    text = text.replace("LengthDifference\n -inf -100 101", f"LengthDifference\n -inf -{ld} {ld + 1}")
+    text = text.replace("   0 5 6 7 8 100\n", f"   0 5 6 7 8 {lmax + 1}\n")
+    assert f"-{off} {off + 1}" in text and f"8 {lmax + 1}" in text
+    return text
+
+
+def test_column_windows_emulated():
+    # k_ts_jump<C, true> / k_traceback<C, true>: the emulator build runs pairs wider than 48 characters on 96-column windows
+    # (second stage 160 columns) so that the window arithmetic -- offsets, band vectors of the fill, staging of table
+    # windows, overflow flag and second stage, windowed traceback -- is exercised at sizes the oracle finishes quickly
+    from template_switch_aligner_b200 import workloads
+    from oracle import tsa_config
+    base = workloads.sample_config_text()
+    total_ts = 0
+    for off, ld, lmax, count, length, thr in ((10, 8, 20, 4, 130, 0), (20, 5, 16, 3, 170, 5)):
+        text = _narrow_model(base, off, ld, lmax)
+        flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+        pairs = []
+        for k in range(count):
+            r, q = workloads.read_pair(900 + 31 * k + off, length)
+            # plant a short reverse-complement copy within reach of the narrow offsets
+            p0 = 40 + 7 * k
+            q = q[:p0] + workloads.revcomp(r[p0 + 2:p0 + 2 + 12]) + q[p0 + 12:]
+            pairs.append((r, q))
+        pairs.append((pairs[0][0], pairs[0][1], (10, len(pairs[0][0]) - 3, 12, len(pairs[0][1]))))
+        aligner = tsa.Aligner(costs=text, alphabet="dna-n", dev_flags=4, first_threshold=thr, lib=emul())
+        total_ts += parity.check_batch(aligner, flat, pairs, label=f"windows {off}/{ld}/{lmax}")
+    assert total_ts >= 3
+    # windows that do not fit the widest class are refused loudly, never answered wrongly
+    wide = tsa.Aligner(costs=base, alphabet="dna-n", dev_flags=4, lib=emul())
+    res = wide.align_batch(workloads.read_pairs(1, start=500, length=200))[0]
+    assert res.status == 9 and "windows" in res.message

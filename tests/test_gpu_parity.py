@@ -97,6 +97,9 @@ def test_reference_kats_gpu(lib, configs, kats):
     assert tsa.cigar_of(res.ops) == k["cigar"]   # 1D2=2I: the reference's own tie-break happens to agree here
 
 
+GOLDEN_TOML_OPTIMA = {"twin_ari_chrX_146823507_146823598.toml": 4}
+
+
 def test_golden_toml_costs_gpu(lib, configs, toml_golden):
     # The committed result files of the reference (test_files/*.toml): same sequences, same range (the offsets in
     # the file and the end point its alignment reaches) -> exactly the recorded optimal cost.
@@ -114,9 +117,13 @@ def test_golden_toml_costs_gpu(lib, configs, toml_golden):
         rng = (p["reference_offset"], er, p["query_offset"], eq)
         aligner = tsa.Aligner(costs=configs[g["config"]], alphabet=ocfg.alphabet, no_ts="no_ts" in name, lib=lib)
         res = aligner.align_batch([(seqs["reference"], seqs["query"], rng)])[0]
-        if res.status != 0:
-            continue  # longer than the widest jump kernel of this build
-        assert res.found and res.cost == int(p["cost"]), (name, res.cost, p["cost"])
+        assert res.status == 0, (name, res.status, res.message)
+        # The files are fixtures of `tsalign show`; nothing in the reference says which cost model produced them.  Under
+        # the sample model the recorded alignment of the 1.1 kb pair (three switches, cost 6) is not optimal: two switches
+        # with a free length difference of 100 cost 4 (rescored below with the compute_cost restatement, and equal to the
+        # scalar DP oracle's optimum, tests/golden/long_costs.json "golden|twin_ari_chrX").
+        want = GOLDEN_TOML_OPTIMA.get(name, int(p["cost"]))
+        assert res.found and res.cost == want and want <= int(p["cost"]), (name, res.cost, p["cost"])
         parity.check_alignment(flat, (seqs["reference"], seqs["query"], rng), res, name)
         checked += 1
     assert checked >= 5
@@ -163,10 +170,7 @@ def test_edge_cases_gpu(lib, configs):
     res = aligner.align_batch([("ACGX", "ACGT"), ("ACGT", "ACGT", (3, 2, 0, 4)), ("ACGT", "ACGT")])
     assert [r.status for r in res] == [7, 8, 0] and res[2].cost == 0
     assert aligner.align_batch([]) == []
-    # a 1.5 kb pair with template switches enabled is refused loudly in this build, and runs with --no-ts
     r, q = workloads.long_pair(0, 1500)
-    res = aligner.align_batch([(r, q)])[0]
-    assert res.status == 9
     nots = tsa.Aligner(costs=configs["sample"], no_ts=True, lib=lib)
     want = oracle.dp_align(flat, r, q, no_ts=True)
     assert nots.align_batch([(r, q)])[0].cost == want.cost
@@ -189,3 +193,51 @@ def test_no_ts_long_gpu(lib):
     r, q = workloads.long_pair(0, 10000)
     nots = tsa.Aligner(costs=text, no_ts=True, lib=lib)
     parity.check_batch(nots, flat, [(r, q)], no_ts=True, label="wave10k")
+
+
+def _long_case(length, index, n_tsm):
+    return workloads.long_pair(index, length, sub_rate=0.004, indel_rate=0.002, n_tsm=n_tsm)
+
+
+def test_column_windows_gpu(lib):
+    # Pairs wider than 544 characters run the jump kernel on column windows (k_ts_jump<17, true>, second stage whole
+    # sequences up to 1055 characters, 1056-column windows beyond).  (1) medium pairs: the windowed path must return the
+    # same optimum as the whole-sequence path (dev_flags=2), which the oracle tests pin; (2) the precomputed oracle costs
+    # of tests/golden/long_costs.json (scalar DP, minutes per pair on a CPU); (3) every alignment rescored.
+    import json
+    import os
+    text = workloads.sample_config_text()
+    flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+    win = tsa.Aligner(costs=text, lib=lib)
+    plain = tsa.Aligner(costs=text, dev_flags=2, lib=lib)
+    medium = [_long_case(600 + 45 * k, 20 + k, 2 + k % 3) for k in range(10)]
+    a = win.align_batch(medium)
+    b = plain.align_batch(medium)
+    assert all(x.status == 0 and y.status == 0 for x, y in zip(a, b)), [(x.status, x.message) for x in a]
+    assert [x.cost for x in a] == [y.cost for y in b]
+    assert sum(x.template_switches > 0 for x in a) >= 5
+    for p, g in zip(medium, a):
+        parity.check_alignment(flat, p, g, "windows medium")
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "long_costs.json")))
+    cases, want = [], []
+    for key, cost in sorted(golden.items()):
+        length, index, n_tsm = map(int, key.split("|"))
+        cases.append(_long_case(length, index, n_tsm)); want.append(cost)
+    assert len(cases) >= 1
+    parity.check_batch(win, flat, cases, label="windows golden", expected=want)
+    # long pairs beyond any whole-sequence class.  With the sample cost model a template switch may shift the diagonal by
+    # +-100 columns for free, so the band of cheap cells grows with every layer: pairs whose optimum needs few switches
+    # fit the 1056-column windows; the others are refused loudly (status 9), never answered wrongly.
+    easy = [workloads.long_pair(60 + k, 1500 + 900 * k, sub_rate=0.0005, indel_rate=0.0, n_tsm=1) for k in range(3)]
+    res = win.align_batch(easy)
+    nots = tsa.Aligner(costs=text, no_ts=True, lib=lib).align_batch(easy)
+    for p, g, h in zip(easy, res, nots):
+        assert g.status == 0 and g.found, (g.status, g.message)
+        assert g.cost <= h.cost
+        parity.check_alignment(flat, p, g, "windows long")
+    assert sum(g.template_switches > 0 for g in res) >= 2
+    hard = [_long_case(3000, 41, 4)]
+    g = win.align_batch(hard)[0]
+    assert g.status in (0, 9)
+    if g.status == 0:
+        parity.check_alignment(flat, hard[0], g, "windows hard")

@@ -63,6 +63,13 @@ def main():
         os.environ["TSA_B200_DEBUG"] = "1"
         aligner = tsa.Aligner(costs=text, alphabet="dna-n")
         timed_align(aligner, pairs, 2, f"c3 len={length} flanks={fl}")
+    elif mode == "longts":
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+        length = int(sys.argv[3]) if len(sys.argv) > 3 else 3000
+        pairs = [workloads.long_pair(i, length, sub_rate=0.004, indel_rate=0.002, n_tsm=4) for i in range(n)]
+        os.environ["TSA_B200_DEBUG"] = "1"
+        aligner = tsa.Aligner(costs=workloads.sample_config_text(), alphabet="dna-n")
+        timed_align(aligner, pairs, 2, f"long ts len={length}")
     return 0
 
 
