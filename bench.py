@@ -227,7 +227,9 @@ def run_ours(args):
     import ctypes as C
     from template_switch_aligner_b200 import api
     arr, keep = api._make_pairs(pairs)
-    opt = api._options(False, local, None, None, first_threshold=args.first_threshold, traceback=True, scout=args.scout)
+    # like `tsalign align`: extension beyond the range and equal-cost ranges of every switch (a_star_aligner.rs:238-253)
+    opt = api._options(False, local, None, None, first_threshold=args.first_threshold, traceback=True, scout=args.scout,
+                       postprocess=api.POST_EXTEND_BEYOND_RANGE | api.POST_EQUAL_COST_RANGES)
     err = C.create_string_buffer(512)
 
     def abi_call():

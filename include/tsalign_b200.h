@@ -66,7 +66,15 @@ typedef struct {
     int32_t first_threshold;       /* 0 = default (12): first pruning threshold of the iterative deepening; tuning only, never changes results */
     int32_t no_traceback;          /* 1 = costs only (ops == NULL) */
     int32_t reserved;
+    int32_t postprocess;           /* TSA_POST_* bits: what template_switch_distance_a_star_align does after the search (a_star_aligner.rs:238-253) */
+    int32_t reserved2;
 } tsa_options;
+
+/* tsa_options.postprocess (host work per found alignment, O(length^2) like the reference's) */
+enum {
+    TSA_POST_EXTEND_BEYOND_RANGE = 1, /* extend_beyond_range_without_increasing_cost (alignment_result.rs:247-395); `tsalign align` default */
+    TSA_POST_EQUAL_COST_RANGES = 2    /* compute_ts_equal_cost_ranges (alignment_result.rs:398-573); the reference always does this */
+};
 
 /* ---- one alignment problem: the arguments of Aligner::align (configurable_a_star_align.rs:214-236) ------ */
 typedef struct {
@@ -94,6 +102,8 @@ typedef struct {
     int32_t secondary;   /* entrance */
     int32_t direction;   /* entrance: 0 = Forward, 1 = Reverse */
     int64_t value;       /* entrance: first_offset; exit: anti_primary_gap */
+    int8_t min_start, max_start, min_end, max_end; /* entrance: EqualCostRange (alignment_type.rs:77-99); (1,-1,1,-1) = invalid / not computed */
+    int32_t reserved;
 } tsa_op;
 
 typedef struct {
@@ -106,6 +116,8 @@ typedef struct {
     size_t n_ops;
     double duration_seconds;   /* share of the batch's wall time */
     char message[96];          /* human-readable reason when status != TSA_OK */
+    int64_t reference_offset, reference_limit; /* the alignment range the ops span (wider than the input range after TSA_POST_EXTEND_BEYOND_RANGE) */
+    int64_t query_offset, query_limit;
 } tsa_result;
 
 /* Batch form of template_switch_distance_a_star_align: aligns n independent pairs on one GPU. */
@@ -126,6 +138,19 @@ void tsa_batch_free(tsa_batch* batch);
 
 /* Integer roofline probe: measured issue rate (lanes/s) of the DPX add-min instructions on all SMs. */
 int tsa_measure_addmin_peak(int device, double* s16x2_lane_ops_per_s, double* s32_lane_ops_per_s);
+
+/* Host-only entry of the post-processing (no device needed): ops in / out in place, `cap` = capacity of the ops array
+ * (the run-length encoding can grow by a few entries), *n_ops updated; range in / out.  Returns TSA_OK, or TSA_ERR_ARGUMENT when
+ * the capacity is too small or a character is not in the alphabet.  Used by the CLI's tests against the reference's result files. */
+int tsa_postprocess(const tsa_config* cfg, const tsa_pair* pair, int32_t postprocess, tsa_op* ops, size_t* n_ops, size_t cap,
+                    int64_t* reference_offset, int64_t* reference_limit, int64_t* query_offset, int64_t* query_limit, uint64_t* cost);
+
+/* The four single-step moves compute_ts_equal_cost_ranges is built from (Alignment::move_template_switch_{start,end}_{backwards,
+ * forwards}, alignment/template_switch_specifics.rs:30-589), host-only, exposed so that the reference's own unit vectors for them
+ * (ibid. :1251-1410) can be replayed: which = 0 start backwards, 1 start forwards, 2 end backwards, 3 end forwards; *compact_index
+ * points at the entrance and follows it.  Returns 1 if the move was possible, 0 if not, < 0 (-TSA_ERR_*) on bad arguments. */
+int tsa_post_move(const tsa_config* cfg, const tsa_pair* pair, int which, tsa_op* ops, size_t* n_ops, size_t cap,
+                  int64_t reference_offset, int64_t query_offset, size_t* compact_index, uint64_t* cost);
 
 /* ---- misc ----------------------------------------------------------------------------------------------- */
 int tsa_device_count(void);

@@ -29,13 +29,14 @@ OP_NAMES = [
 EXPORTS = [
     "tsa_config_parse", "tsa_config_default", "tsa_config_write", "tsa_config_free", "tsa_config_alphabet",
     "tsa_align_batch", "tsa_results_free", "tsa_batch_create", "tsa_batch_run", "tsa_batch_fetch", "tsa_batch_stats",
-    "tsa_batch_free", "tsa_batch_timing", "tsa_batch_work", "tsa_measure_addmin_peak", "tsa_device_count", "tsa_version",
+    "tsa_batch_free", "tsa_batch_timing", "tsa_batch_work", "tsa_measure_addmin_peak", "tsa_postprocess", "tsa_post_move", "tsa_device_count", "tsa_version",
 ]
 
 
 class TsaOptions(C.Structure):
     _fields_ = [("no_ts", C.c_int32), ("device", C.c_int32), ("cost_limit", C.c_uint64), ("memory_limit", C.c_uint64),
-                ("max_template_switches", C.c_int32), ("first_threshold", C.c_int32), ("no_traceback", C.c_int32), ("reserved", C.c_int32)]
+                ("max_template_switches", C.c_int32), ("first_threshold", C.c_int32), ("no_traceback", C.c_int32), ("reserved", C.c_int32),
+                ("postprocess", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class TsaPair(C.Structure):
@@ -45,13 +46,15 @@ class TsaPair(C.Structure):
 
 class TsaOp(C.Structure):
     _fields_ = [("count", C.c_int64), ("type", C.c_int32), ("primary", C.c_int32), ("secondary", C.c_int32),
-                ("direction", C.c_int32), ("value", C.c_int64)]
+                ("direction", C.c_int32), ("value", C.c_int64),
+                ("min_start", C.c_int8), ("max_start", C.c_int8), ("min_end", C.c_int8), ("max_end", C.c_int8), ("reserved", C.c_int32)]
 
 
 class TsaResult(C.Structure):
     _fields_ = [("status", C.c_int32), ("result_type", C.c_int32), ("cost", C.c_uint64), ("template_switches", C.c_int32),
                 ("reserved", C.c_int32), ("ops", C.POINTER(TsaOp)), ("n_ops", C.c_size_t), ("duration_seconds", C.c_double),
-                ("message", C.c_char * 96)]
+                ("message", C.c_char * 96),
+                ("reference_offset", C.c_int64), ("reference_limit", C.c_int64), ("query_offset", C.c_int64), ("query_limit", C.c_int64)]
 
 
 class TsaError(RuntimeError):
@@ -92,6 +95,11 @@ def bind(cdll):
     cdll.tsa_measure_addmin_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     cdll.tsa_batch_free.restype = None
     cdll.tsa_batch_free.argtypes = [C.c_void_p]
+    cdll.tsa_postprocess.restype = C.c_int
+    cdll.tsa_postprocess.argtypes = [C.c_void_p, C.POINTER(TsaPair), C.c_int32, C.POINTER(TsaOp), C.POINTER(C.c_size_t), C.c_size_t] + [C.POINTER(C.c_int64)] * 4 + [C.POINTER(C.c_uint64)]
+    cdll.tsa_post_move.restype = C.c_int
+    cdll.tsa_post_move.argtypes = [C.c_void_p, C.POINTER(TsaPair), C.c_int, C.POINTER(TsaOp), C.POINTER(C.c_size_t), C.c_size_t, C.c_int64, C.c_int64,
+                                   C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
     cdll.tsa_device_count.restype = C.c_int
     cdll.tsa_device_count.argtypes = []
     cdll.tsa_version.restype = C.c_char_p

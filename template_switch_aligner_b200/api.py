@@ -106,7 +106,7 @@ def _make_pairs(pairs: Sequence[tuple]):
     return arr, keep
 
 
-def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0, traceback=True, scout=False, dev_flags=0) -> TsaOptions:
+def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0, traceback=True, scout=False, dev_flags=0, postprocess=0) -> TsaOptions:
     o = TsaOptions()
     o.no_ts = int(bool(no_ts))
     o.device = device
@@ -116,27 +116,41 @@ def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_temp
     o.first_threshold = first_threshold
     o.no_traceback = 0 if traceback else 1
     o.reserved = (1 if scout else 0) | (dev_flags & ~1)   # developer knobs of the engine (tsa_capi.cpp: engine_options)
+    o.postprocess = int(postprocess)
     return o
 
 
-_OP_STRUCT = struct.Struct("<qiiiiq")  # tsa_op: count, type, primary, secondary, direction, value
+_OP_STRUCT = struct.Struct("<qiiiiqbbbbi")  # tsa_op: count, type, primary, secondary, direction, value, equal-cost range, reserved
+POST_EXTEND_BEYOND_RANGE, POST_EQUAL_COST_RANGES = 1, 2   # TSA_POST_* of include/tsalign_b200.h
 
 
 class BatchResult:
     """One entry of a batch: the C struct tsa_result, copied out.  `ops` (the run-length encoded alignment as
     (count, type, primary, secondary, direction, value) tuples) is decoded on first use."""
-    __slots__ = ("status", "result_type", "cost", "template_switches", "message", "duration_seconds", "_raw", "_ops")
+    __slots__ = ("status", "result_type", "cost", "template_switches", "message", "duration_seconds", "range", "_raw", "_ops", "_ecr")
 
-    def __init__(self, status, result_type, cost, template_switches, raw_ops, message="", duration_seconds=0.0):
+    def __init__(self, status, result_type, cost, template_switches, raw_ops, message="", duration_seconds=0.0, rng=None):
         self.status, self.result_type, self.cost, self.template_switches = status, result_type, cost, template_switches
         self.message, self.duration_seconds = message, duration_seconds
-        self._raw, self._ops = raw_ops, None
+        self.range = rng                      # (reference_offset, reference_limit, query_offset, query_limit) the ops span
+        self._raw, self._ops, self._ecr = raw_ops, None, None
+
+    def _decode(self):
+        if self._ops is None and self._raw is not None:
+            rows = list(_OP_STRUCT.iter_unpack(self._raw))
+            self._ops = [r[:6] for r in rows]
+            self._ecr = [r[6:10] if r[1] == 12 else None for r in rows]
 
     @property
     def ops(self) -> Optional[List[Tuple[int, int, int, int, int, int]]]:
-        if self._ops is None and self._raw is not None:
-            self._ops = list(_OP_STRUCT.iter_unpack(self._raw))
+        self._decode()
         return self._ops
+
+    @property
+    def equal_cost_ranges(self) -> Optional[List[Optional[Tuple[int, int, int, int]]]]:
+        """Per op: (min_start, max_start, min_end, max_end) of a template switch entrance, else None."""
+        self._decode()
+        return self._ecr
 
     @property
     def found(self) -> bool:
@@ -155,22 +169,73 @@ def _copy_results(lib, res, n) -> List[BatchResult]:
         r = res[i]
         raw = C.string_at(r.ops, r.n_ops * size) if r.ops else None
         out.append(BatchResult(r.status, names[r.result_type], r.cost, r.template_switches, raw,
-                               r.message.decode(errors="replace") if r.status else "", r.duration_seconds))
+                               r.message.decode(errors="replace") if r.status else "", r.duration_seconds,
+                               (r.reference_offset, r.reference_limit, r.query_offset, r.query_limit)))
     lib.tsa_results_free(res, n)
     return out
 
 
-def cigar_of(ops) -> str:
-    """Alignment::cigar (alignment.rs:95-110, template_switch_distance/display.rs:8-41); equal-cost ranges invalid."""
+def cigar_of(ops, ranges=None) -> str:
+    """Alignment::cigar (alignment.rs:95-110, template_switch_distance/display.rs:8-41,80-94)."""
     out = []
-    for count, t, p, s, d, v in ops:
+    for idx, (count, t, p, s, d, v) in enumerate(ops):
         if t == 12:
-            out.append("[TS%s%s%s:[-]:[-]:%d:" % ("RQ"[p], "RQ"[s], "FR"[d], v))
+            e = ranges[idx] if ranges else None
+            valid = e is not None and e[0] <= e[1] and e[2] <= e[3]      # EqualCostRange::is_valid
+            rng = "[%d,%d]:[%d,%d]" % tuple(e) if valid else "[-]:[-]"
+            out.append("[TS%s%s%s:%s:%d:" % ("RQ"[p], "RQ"[s], "FR"[d], rng, v))
         elif t == 13:
             out.append(":%d]" % v)
         else:
             out.append("%d%s" % (count, "IDX="[t & 3]))
     return "".join(out)
+
+
+def _ops_array(ops, ranges=None, extra=16):
+    """[(count, type, primary, secondary, direction, value)] (+ equal-cost ranges) -> (TsaOp array with spare capacity, n)."""
+    arr = (TsaOp * (len(ops) + extra))()
+    for i, o in enumerate(ops):
+        a = arr[i]
+        a.count, a.type, a.primary, a.secondary, a.direction, a.value = o[:6]
+        e = (ranges[i] if ranges and ranges[i] is not None else (1, -1, 1, -1)) if o[1] == 12 else (0, 0, 0, 0)
+        a.min_start, a.max_start, a.min_end, a.max_end = e
+    return arr
+
+
+def _ops_list(arr, n):
+    ops = [(arr[i].count, arr[i].type, arr[i].primary, arr[i].secondary, arr[i].direction, arr[i].value) for i in range(n)]
+    ranges = [(arr[i].min_start, arr[i].max_start, arr[i].min_end, arr[i].max_end) if arr[i].type == 12 else None for i in range(n)]
+    return ops, ranges
+
+
+def postprocess(config: "Config", reference, query, ops, rng, flags: int, ranges=None):
+    """Host-only: what the reference does to a found alignment after the search (a_star_aligner.rs:238-253).
+    rng = (reference_offset, reference_limit, query_offset, query_limit).  Returns (ops, equal-cost ranges, range, cost)."""
+    lib = config._lib
+    arr_p, keep = _make_pairs([(reference, query)])
+    arr = _ops_array(ops, ranges, extra=len(ops) + 64)
+    n = C.c_size_t(len(ops))
+    r = [C.c_int64(x) for x in rng]
+    cost = C.c_uint64(0)
+    rc = lib.tsa_postprocess(config._h, arr_p, flags, arr, C.byref(n), len(arr), C.byref(r[0]), C.byref(r[1]), C.byref(r[2]), C.byref(r[3]), C.byref(cost))
+    if rc != 0:
+        raise TsaError(rc, "tsa_postprocess")
+    out_ops, out_ranges = _ops_list(arr, n.value)
+    return out_ops, out_ranges, tuple(x.value for x in r), cost.value
+
+
+def post_move(config: "Config", reference, query, which: int, ops, ref_offset: int, qry_offset: int, compact_index: int):
+    """Host-only single move of a template switch boundary (tsa_post_move).  Returns (moved, ops, compact_index, cost)."""
+    lib = config._lib
+    arr_p, keep = _make_pairs([(reference, query)])
+    arr = _ops_array(ops, None, extra=8)
+    n = C.c_size_t(len(ops))
+    ci = C.c_size_t(compact_index)
+    cost = C.c_uint64(0)
+    rc = lib.tsa_post_move(config._h, arr_p, which, arr, C.byref(n), len(arr), ref_offset, qry_offset, C.byref(ci), C.byref(cost))
+    if rc < 0:
+        raise TsaError(-rc, "tsa_post_move")
+    return bool(rc), _ops_list(arr, n.value)[0], ci.value, cost.value
 
 
 class Alignment:
@@ -190,16 +255,17 @@ class Alignment:
     def cigar(self) -> Optional[str]:
         if not self._r.found or self._r.ops is None:
             return None
-        return cigar_of(self._r.ops)
+        return cigar_of(self._r.ops, self._r.equal_cost_ranges)
 
     def alignments(self) -> Optional[List[Tuple[int, AlignmentOp]]]:
         if not self._r.found or self._r.ops is None:
             return None
         out = []
-        for count, t, p, s, d, v in self._r.ops:
+        for (count, t, p, s, d, v), e in zip(self._r.ops, self._r.equal_cost_ranges):
             if t == 12:
+                ecr = dict(zip(("min_start", "max_start", "min_end", "max_end"), e)) if e is not None else dict(_INVALID_RANGE)
                 out.append((count, TemplateSwitchEntranceOp("TemplateSwitchEntrance", v, ["Reference", "Query"][p], ["Reference", "Query"][s],
-                                                            ["Forward", "Reverse"][d], dict(_INVALID_RANGE))))
+                                                            ["Forward", "Reverse"][d], ecr)))
             elif t == 13:
                 out.append((count, TemplateSwitchExitOp("TemplateSwitchExit", v)))
             else:
@@ -238,7 +304,8 @@ class Aligner:
     def __init__(self, *, no_ts: bool = False, min_length_strategy: str = "lookahead", chaining_strategy: str = "none",
                  total_length_strategy: str = "maximise", costs: Optional[str] = None,
                  costs_file: Optional[Union[str, pathlib.Path]] = None, alphabet: str = "dna-n", device: int = 0,
-                 first_threshold: int = 0, traceback: bool = True, scout: bool = False, dev_flags: int = 0, lib=None) -> None:
+                 first_threshold: int = 0, traceback: bool = True, scout: bool = False, dev_flags: int = 0,
+                 postprocess: Optional[int] = None, lib=None) -> None:
         if costs is not None and costs_file is not None:
             raise ValueError("Provide at most one of 'costs' or 'costs_file'.")
         if min_length_strategy not in _MIN_LENGTH:
@@ -254,17 +321,24 @@ class Aligner:
         self.device = device
         self.traceback = bool(traceback)        # False: optimal costs only
         self.scout = bool(scout)                # tuning of the exact pruning only
+        # what happens after the search (a_star_aligner.rs:238-253): None = like the reference's callers -- align() extends
+        # beyond the range and computes equal-cost ranges (python_bindings/src/lib.rs:124-133), align_batch() returns the
+        # searched alignments as they are; an int (POST_* bits) applies to both
+        self.postprocess = postprocess
         self.dev_flags = int(dev_flags)         # developer knobs (2: no column windows for medium pairs; 4: small windows, emulator only)
         self.first_threshold = first_threshold  # tuning of the exact pruning only; results do not depend on it
         self.config = Config(costs, alphabet, lib=self._lib)
 
     # -- batch entry point: the call the GPU path is built for ----------------------------------------------
-    def align_batch(self, pairs: Sequence[tuple], *, cost_limit: Optional[int] = None, memory_limit: Optional[int] = None) -> List[BatchResult]:
+    def align_batch(self, pairs: Sequence[tuple], *, cost_limit: Optional[int] = None, memory_limit: Optional[int] = None,
+                    postprocess: Optional[int] = None) -> List[BatchResult]:
         """Align independent pairs: [(reference, query) or (reference, query, (ref_offset, ref_limit, qry_offset, qry_limit))]."""
         arr, keep = _make_pairs(pairs)
         res = (TsaResult * max(1, len(pairs)))()
         err = C.create_string_buffer(512)
-        opt = _options(self.no_ts, self.device, cost_limit, memory_limit, first_threshold=self.first_threshold, traceback=self.traceback, scout=self.scout, dev_flags=self.dev_flags)
+        post = postprocess if postprocess is not None else (self.postprocess or 0)
+        opt = _options(self.no_ts, self.device, cost_limit, memory_limit, first_threshold=self.first_threshold, traceback=self.traceback, scout=self.scout,
+                       dev_flags=self.dev_flags, postprocess=post)
         rc = self._lib.tsa_align_batch(self.config._h, C.byref(opt), arr, len(pairs), res, err, len(err))
         if rc != 0:
             raise TsaError(rc, err.value.decode(errors="replace"))
@@ -281,18 +355,18 @@ class Aligner:
             query_start, query_limit = range.query_start, range.query_end
         r, q = _clean(reference), _clean(query)
         rng = (reference_start or 0, reference_limit, query_start or 0, query_limit)
-        res = self.align_batch([(r, q, rng)], cost_limit=cost_limit, memory_limit=memory_limit)[0]
+        post = self.postprocess if self.postprocess is not None else POST_EXTEND_BEYOND_RANGE | POST_EQUAL_COST_RANGES
+        res = self.align_batch([(r, q, rng)], cost_limit=cost_limit, memory_limit=memory_limit, postprocess=post)[0]
         if res.status != 0:
             raise TsaError(res.status, res.message)
         if not res.found:
             return None
-        full = (rng[0], len(r) if rng[1] is None else rng[1], rng[2], len(q) if rng[3] is None else rng[3])
-        return Alignment(res, r, q, (reference_name, query_name), full, self.config.alphabet)
+        return Alignment(res, r, q, (reference_name, query_name), res.range, self.config.alphabet)
 
 
 def align(reference: object, query: object, **kwargs: object) -> Optional[Alignment]:
     """One-call convenience wrapper (mirror of tsalign.align)."""
-    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib", "first_threshold", "traceback", "scout", "dev_flags")}
+    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib", "first_threshold", "traceback", "scout", "dev_flags", "postprocess")}
     align_kwargs = {k: v for k, v in kwargs.items() if k not in aligner_kwargs}
     return Aligner(**aligner_kwargs).align(reference, query, **align_kwargs)
 
@@ -307,7 +381,8 @@ class StagedBatch:
         arr, keep = _make_pairs(pairs)
         status = C.c_int(0)
         err = C.create_string_buffer(512)
-        opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit, first_threshold=aligner.first_threshold, traceback=aligner.traceback, scout=aligner.scout, dev_flags=aligner.dev_flags)
+        opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit, first_threshold=aligner.first_threshold, traceback=aligner.traceback, scout=aligner.scout,
+                       dev_flags=aligner.dev_flags, postprocess=aligner.postprocess or 0)
         self._h = self._lib.tsa_batch_create(aligner.config._h, C.byref(opt), arr, self.n, C.byref(status), err, len(err))
         if not self._h:
             raise TsaError(status.value, err.value.decode(errors="replace"))

@@ -9,11 +9,14 @@
 
 #include "tsa_config.hpp"
 #include "tsa_engine.hpp"
+#include "tsa_post.hpp"
 #include "tsa_rt.hpp"
 
 using namespace tsa;
 
+#include <atomic>
 #include <mutex>
+#include <thread>
 
 // A parsed cost model plus the engines (device buffers, stream) that tsa_align_batch reuses from call to call.
 struct tsa_config {
@@ -116,6 +119,7 @@ void assemble_ops(tsa_result& r, const PairCost& pc) {
         op.type = u; op.count = 1;
         out.push_back(op);
     }
+    for (tsa_op& op : out) if (op.type == TSA_OP_TS_ENTRANCE) { op.min_start = 1; op.max_start = -1; op.min_end = 1; op.max_end = -1; }   // EqualCostRange::new_invalid()
     r.n_ops = out.size();
     r.ops = (tsa_op*)malloc(sizeof(tsa_op) * std::max<size_t>(1, out.size()));
     memcpy(r.ops, out.data(), sizeof(tsa_op) * out.size());
@@ -142,6 +146,48 @@ void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
     case PAIR_ERR_FLANKS: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "flank lengths above 255 are not supported"); break;
     default: r.status = TSA_ERR_ARGUMENT; break;
     }
+}
+
+std::vector<PostOp> to_post(const tsa_op* ops, size_t n) {
+    std::vector<PostOp> v(n);
+    for (size_t i = 0; i < n; i++) {
+        v[i].count = ops[i].count; v[i].type = ops[i].type; v[i].primary = ops[i].primary; v[i].secondary = ops[i].secondary;
+        v[i].direction = ops[i].direction; v[i].value = ops[i].value;
+        v[i].ecr[0] = ops[i].min_start; v[i].ecr[1] = ops[i].max_start; v[i].ecr[2] = ops[i].min_end; v[i].ecr[3] = ops[i].max_end;
+    }
+    return v;
+}
+void from_post(const std::vector<PostOp>& v, tsa_op* ops) {
+    for (size_t i = 0; i < v.size(); i++) {
+        memset(&ops[i], 0, sizeof(tsa_op));
+        ops[i].count = v[i].count; ops[i].type = v[i].type; ops[i].primary = v[i].primary; ops[i].secondary = v[i].secondary;
+        ops[i].direction = v[i].direction; ops[i].value = v[i].value;
+        ops[i].min_start = v[i].ecr[0]; ops[i].max_start = v[i].ecr[1]; ops[i].min_end = v[i].ecr[2]; ops[i].max_end = v[i].ecr[3];
+    }
+}
+
+// a_star_aligner.rs:238-253 on one found alignment (encoded sequences of the pair)
+void postprocess_result(const HostConfig& cfg, const PairView& pv, int32_t flags, tsa_result& r) {
+    if (!flags || r.status != TSA_OK || r.result_type != TSA_FOUND_TARGET || !r.ops) return;
+    std::vector<PostOp> ops = to_post(r.ops, r.n_ops);
+    int64_t ro = r.reference_offset, rl = r.reference_limit, qo = r.query_offset, ql = r.query_limit;
+    if (flags & TSA_POST_EXTEND_BEYOND_RANGE) post_extend_beyond_range(cfg, pv.ref, pv.n, pv.qry, pv.m, ops, ro, rl, qo, ql);
+    if (flags & TSA_POST_EQUAL_COST_RANGES) post_equal_cost_ranges(cfg, pv.ref, pv.n, pv.qry, pv.m, ops, ro, qo);
+    if (ops.size() != r.n_ops) { free(r.ops); r.ops = (tsa_op*)malloc(sizeof(tsa_op) * std::max<size_t>(1, ops.size())); r.n_ops = ops.size(); }
+    from_post(ops, r.ops);
+    r.reference_offset = ro; r.reference_limit = rl; r.query_offset = qo; r.query_limit = ql;
+}
+
+// Result assembly (run-length encoding, post-processing) of a batch on the host cores.
+template <class F>
+void parallel_for(size_t n, F&& body) {
+    const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), (n + 255) / 256);
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) body(i); return; }
+    std::vector<std::thread> th;
+    std::atomic<size_t> next(0);
+    for (size_t t = 0; t < nt; t++) th.emplace_back([&]() { for (;;) { const size_t lo = next.fetch_add(64); if (lo >= n) break; for (size_t i = lo; i < std::min(n, lo + 64); i++) body(i); } });
+    for (auto& x : th) x.join();
 }
 
 AlignOptions engine_options(const tsa_options& o) {
@@ -199,6 +245,7 @@ int tsa_config_alphabet(const tsa_config* cfg) { return cfg ? cfg->host.alphabet
 }  // extern "C"
 
 struct tsa_batch {
+    HostConfig host;
     std::unique_ptr<Engine> engine;
     Encoded enc;
     tsa_options opt;
@@ -214,6 +261,7 @@ tsa_batch* tsa_batch_create(const tsa_config* cfg, const tsa_options* opt, const
     std::unique_ptr<tsa_batch> b(new tsa_batch);
     b->opt = opt ? *opt : default_options();
     b->n = n;
+    b->host = cfg->host;
     b->engine.reset(new Engine(cfg->host, b->opt.device));
     if (!b->engine->ok()) {
         *status = b->engine->error().find("CUDA") != std::string::npos ? TSA_ERR_NO_DEVICE : TSA_ERR_UNSUPPORTED;
@@ -250,7 +298,13 @@ int tsa_batch_fetch(tsa_batch* b, tsa_result* out) try {
         out[i].status = b->enc.pair_status[i];
         snprintf(out[i].message, sizeof(out[i].message), "%s", b->enc.pair_msg[i].c_str());
     }
-    for (size_t k = 0; k < b->enc.live.size(); k++) fill_result(out[b->enc.live[k]], b->costs[k], b->opt);
+    parallel_for(b->enc.live.size(), [&](size_t k) {
+        tsa_result& r = out[b->enc.live[k]];
+        fill_result(r, b->costs[k], b->opt);
+        const PairView& pv = b->enc.views[k];
+        r.reference_offset = pv.ro; r.reference_limit = pv.rl; r.query_offset = pv.qo; r.query_limit = pv.ql;
+        postprocess_result(b->host, pv, b->opt.postprocess, r);
+    });
     return TSA_OK;
 } catch (const std::exception& e) {
     fprintf(stderr, "tsalign_b200: %s\n", e.what());
@@ -320,7 +374,13 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
         out[i].status = enc.pair_status[i];
         snprintf(out[i].message, sizeof(out[i].message), "%s", enc.pair_msg[i].c_str());
     }
-    for (size_t k = 0; k < enc.live.size(); k++) fill_result(out[enc.live[k]], costs[k], o);
+    parallel_for(enc.live.size(), [&](size_t k) {
+        tsa_result& r = out[enc.live[k]];
+        fill_result(r, costs[k], o);
+        const PairView& pv = enc.views[k];
+        r.reference_offset = pv.ro; r.reference_limit = pv.rl; r.query_offset = pv.qo; r.query_limit = pv.ql;
+        postprocess_result(cfg->host, pv, o.postprocess, r);
+    });
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (getenv("TSA_B200_DEBUG"))
         fprintf(stderr, "[tsalign_b200] align_batch n=%zu: encode %.2f ms, engine %.2f ms, results %.2f ms\n", n,
@@ -338,6 +398,53 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
 void tsa_results_free(tsa_result* results, size_t n) {
     if (!results) return;
     for (size_t i = 0; i < n; i++) { free(results[i].ops); results[i].ops = nullptr; results[i].n_ops = 0; }
+}
+
+int tsa_postprocess(const tsa_config* cfg, const tsa_pair* pair, int32_t postprocess, tsa_op* ops, size_t* n_ops, size_t cap,
+                    int64_t* reference_offset, int64_t* reference_limit, int64_t* query_offset, int64_t* query_limit, uint64_t* cost) try {
+    if (!cfg || !pair || !ops || !n_ops || !reference_offset || !reference_limit || !query_offset || !query_limit) return TSA_ERR_ARGUMENT;
+    Encoded enc;
+    encode_pairs(cfg->host, pair, 1, enc);
+    if (enc.views.empty()) return TSA_ERR_ARGUMENT;
+    const PairView& pv = enc.views[0];
+    std::vector<PostOp> v = to_post(ops, *n_ops);
+    int64_t ro = *reference_offset, rl = *reference_limit, qo = *query_offset, ql = *query_limit;
+    if (postprocess & TSA_POST_EXTEND_BEYOND_RANGE) post_extend_beyond_range(cfg->host, pv.ref, pv.n, pv.qry, pv.m, v, ro, rl, qo, ql);
+    if (postprocess & TSA_POST_EQUAL_COST_RANGES) post_equal_cost_ranges(cfg->host, pv.ref, pv.n, pv.qry, pv.m, v, ro, qo);
+    if (cost) *cost = post_compute_cost(cfg->host, pv.ref, pv.n, pv.qry, pv.m, ro, qo, v);
+    if (v.size() > cap) return TSA_ERR_ARGUMENT;
+    from_post(v, ops);
+    *n_ops = v.size();
+    *reference_offset = ro; *reference_limit = rl; *query_offset = qo; *query_limit = ql;
+    return TSA_OK;
+} catch (const std::exception&) {
+    return TSA_ERR_INTERNAL;
+}
+
+int tsa_post_move(const tsa_config* cfg, const tsa_pair* pair, int which, tsa_op* ops, size_t* n_ops, size_t cap,
+                  int64_t reference_offset, int64_t query_offset, size_t* compact_index, uint64_t* cost) try {
+    if (!cfg || !pair || !ops || !n_ops || !compact_index || which < 0 || which > 3) return -TSA_ERR_ARGUMENT;
+    Encoded enc;
+    encode_pairs(cfg->host, pair, 1, enc);
+    if (enc.views.empty()) return -TSA_ERR_ARGUMENT;
+    const PairView& pv = enc.views[0];
+    std::vector<PostOp> v = to_post(ops, *n_ops);
+    size_t ci = *compact_index;
+    bool ok = false;
+    switch (which) {
+    case 0: ok = post_move_start_backwards(pv.ref, pv.n, pv.qry, pv.m, cfg->host.alphabet, reference_offset, query_offset, v, ci); break;
+    case 1: ok = post_move_start_forwards(pv.ref, pv.n, pv.qry, pv.m, reference_offset, query_offset, v, ci); break;
+    case 2: ok = post_move_end_backwards(pv.ref, pv.n, pv.qry, pv.m, reference_offset, query_offset, v, ci); break;
+    default: ok = post_move_end_forwards(pv.ref, pv.n, pv.qry, pv.m, cfg->host.alphabet, reference_offset, query_offset, v, ci); break;
+    }
+    if (cost) *cost = post_compute_cost(cfg->host, pv.ref, pv.n, pv.qry, pv.m, reference_offset, query_offset, v);
+    if (v.size() > cap) return -TSA_ERR_ARGUMENT;
+    from_post(v, ops);
+    *n_ops = v.size();
+    *compact_index = ci;
+    return ok ? 1 : 0;
+} catch (const std::exception&) {
+    return -TSA_ERR_INTERNAL;
 }
 
 int tsa_device_count(void) {

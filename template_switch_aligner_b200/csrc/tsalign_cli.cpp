@@ -96,7 +96,10 @@ std::string cigar(const tsa_result& r) {  // alignment.rs:95-110, template_switc
     for (size_t i = 0; i < r.n_ops; i++) {
         const tsa_op& op = r.ops[i];
         if (op.type == TSA_OP_TS_ENTRANCE) {
-            out += std::string("[TS") + "RQ"[op.primary] + "RQ"[op.secondary] + "FR"[op.direction] + ":[-]:[-]:" + std::to_string(op.value) + ":";
+            // EqualCostRange display (template_switch_distance/display.rs:80-94)
+            const bool valid = op.min_start <= op.max_start && op.min_end <= op.max_end;
+            const std::string rng = valid ? "[" + std::to_string(op.min_start) + "," + std::to_string(op.max_start) + "]:[" + std::to_string(op.min_end) + "," + std::to_string(op.max_end) + "]" : "[-]:[-]";
+            out += std::string("[TS") + "RQ"[op.primary] + "RQ"[op.secondary] + "FR"[op.direction] + ":" + rng + ":" + std::to_string(op.value) + ":";
         } else if (op.type == TSA_OP_TS_EXIT) {
             out += ":" + std::to_string(op.value) + "]";
         } else {
@@ -272,6 +275,8 @@ int main(int argc, char** argv) {
     tsa_options opt;
     memset(&opt, 0, sizeof(opt));
     opt.no_ts = cli.no_ts; opt.device = cli.device; opt.cost_limit = cli.cost_limit; opt.memory_limit = cli.memory_limit;
+    // a_star_aligner.rs:238-253: extension unless --dont-extend-beyond-range, equal-cost ranges always
+    opt.postprocess = TSA_POST_EQUAL_COST_RANGES | (cli.dont_extend ? 0 : TSA_POST_EXTEND_BEYOND_RANGE);
     tsa_pair pair;
     pair.reference = ref.seq.data(); pair.reference_len = ref.seq.size();
     pair.query = qry.seq.data(); pair.query_len = qry.seq.size();
@@ -281,7 +286,7 @@ int main(int argc, char** argv) {
     if (rc != TSA_OK) die(std::string("alignment failed: ") + err);
     if (res.status == TSA_ERR_INVALID_CHAR) die(std::string(strstr(res.message, "reference") ? "Reference" : "Query") + " contains non-alphabet character: " + res.message);
     if (res.status != TSA_OK) die(std::string("alignment failed: ") + res.message);
-    if (!cli.dont_extend) fprintf(stderr, "note: tsalign-b200 does not extend the alignment beyond the given range and reports no equal-cost ranges\n");
+    if (res.status == TSA_OK && res.result_type == TSA_FOUND_TARGET) { ro = res.reference_offset; qo = res.query_offset; }   // statistics follow the extended range
 
     // ---- statistics (alignment_result.rs:175-237) ----
     const bool found = res.result_type == TSA_FOUND_TARGET;
@@ -309,7 +314,8 @@ int main(int argc, char** argv) {
                 if (i) out << ", ";
                 out << "[" << op.count << ", ";
                 if (op.type == TSA_OP_TS_ENTRANCE)
-                    out << "{ TemplateSwitchEntrance = { first_offset = " << op.value << ", equal_cost_range = { min_start = 1, max_start = -1, min_end = 1, max_end = -1 }, primary = \""
+                    out << "{ TemplateSwitchEntrance = { first_offset = " << op.value << ", equal_cost_range = { min_start = " << (int)op.min_start << ", max_start = " << (int)op.max_start
+                        << ", min_end = " << (int)op.min_end << ", max_end = " << (int)op.max_end << " }, primary = \""
                         << (op.primary ? "Query" : "Reference") << "\", secondary = \"" << (op.secondary ? "Query" : "Reference") << "\", direction = \""
                         << (op.direction ? "Reverse" : "Forward") << "\" } }";
                 else if (op.type == TSA_OP_TS_EXIT) out << "{ TemplateSwitchExit = { anti_primary_gap = " << op.value << " } }";

@@ -97,7 +97,10 @@ def test_reference_kats_gpu(lib, configs, kats):
     assert tsa.cigar_of(res.ops) == k["cigar"]   # 1D2=2I: the reference's own tie-break happens to agree here
 
 
-GOLDEN_TOML_OPTIMA = {"twin_ari_chrX_146823507_146823598.toml": 4}
+def _toml_optima():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "toml_optima.json")))
 
 
 def test_golden_toml_costs_gpu(lib, configs, toml_golden):
@@ -105,6 +108,7 @@ def test_golden_toml_costs_gpu(lib, configs, toml_golden):
     # the file and the end point its alignment reaches) -> exactly the recorded optimal cost.
     from helpers import ops_from_toml
     checked = 0
+    optima = _toml_optima()
     for name, g in toml_golden.items():
         p = g["parsed"]
         if p["type"] != "WithTarget":
@@ -121,8 +125,8 @@ def test_golden_toml_costs_gpu(lib, configs, toml_golden):
         # The files are fixtures of `tsalign show`; nothing in the reference says which cost model produced them.  Under
         # the sample model the recorded alignment of the 1.1 kb pair (three switches, cost 6) is not optimal: two switches
         # with a free length difference of 100 cost 4 (rescored below with the compute_cost restatement, and equal to the
-        # scalar DP oracle's optimum, tests/golden/long_costs.json "golden|twin_ari_chrX").
-        want = GOLDEN_TOML_OPTIMA.get(name, int(p["cost"]))
+        # scalar DP oracle's optimum, tests/golden/toml_optima.json written by tests/golden/make_toml_optima.py).
+        want = optima.get(name, int(p["cost"]))
         assert res.found and res.cost == want and want <= int(p["cost"]), (name, res.cost, p["cost"])
         parity.check_alignment(flat, (seqs["reference"], seqs["query"], rng), res, name)
         checked += 1

@@ -63,6 +63,30 @@ def main():
         os.environ["TSA_B200_DEBUG"] = "1"
         aligner = tsa.Aligner(costs=text, alphabet="dna-n")
         timed_align(aligner, pairs, 2, f"c3 len={length} flanks={fl}")
+    elif mode == "c5":
+        # BASELINE config 5 shape without template switches: one 230 147 x 236 216 pair on one GPU
+        n_len = int(sys.argv[2]) if len(sys.argv) > 2 else 230147
+        import random
+        rnd = random.Random(5)
+        ref = "".join(rnd.choice("ACGT") for _ in range(n_len))
+        out = []
+        i = 0
+        while i < n_len:
+            x = rnd.random()
+            if x < 0.0015:
+                i += 1 + int(rnd.expovariate(1 / 4.0)); continue
+            if x < 0.003:
+                out.extend(rnd.choice("ACGT") for _ in range(1 + int(rnd.expovariate(1 / 4.0))))
+            c = ref[i]
+            if rnd.random() < 0.012:
+                c = rnd.choice([b for b in "ACGT" if b != c])
+            out.append(c); i += 1
+        qry = "".join(out)
+        print("lengths", len(ref), len(qry), flush=True)
+        os.environ["TSA_B200_DEBUG"] = "1"
+        for tb in (False, True):
+            aligner = tsa.Aligner(costs=workloads.sample_config_text(), alphabet="dna-n", no_ts=True, traceback=tb)
+            timed_align(aligner, [(ref, qry)], 2, f"c5 no-ts traceback={tb}")
     elif mode == "longts":
         n = int(sys.argv[2]) if len(sys.argv) > 2 else 8
         length = int(sys.argv[3]) if len(sys.argv) > 3 else 3000
