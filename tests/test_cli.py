@@ -75,8 +75,12 @@ def test_without_target_and_flags(workdir, toml_golden):
     assert set(doc) == set(golden) and doc["result"] == {"astar_result_type": "ExceededCostLimit", "cost_limit": 0}
     # heuristic flags of the reference are accepted and ignored; ranges; skip characters; separate files
     r = run(workdir, "align", "-p", "test_files/twin_10_ts.fa", "--ts-min-length-strategy", "none", "--ts-total-length-strategy=none",
-            "--ts-node-ord-strategy", "anti-diagonal", "--rq-ranges", "R2..8Q2..8", "--skip-characters", "-", "-l", "debug")
+            "--ts-node-ord-strategy", "anti-diagonal", "--rq-ranges", "R2..8Q2..8", "--skip-characters", "-", "-l", "debug", "--dont-extend-beyond-range")
     assert r.returncode == 0 and "Reference offset: 2" in r.stdout
+    # by default the alignment is extended beyond the range while the cost does not increase (alignment_result.rs:247-395):
+    # here over the two matching characters on either side, so the reported offsets move to 0
+    r = run(workdir, "align", "-p", "test_files/twin_10_ts.fa", "--rq-ranges", "R2..8Q2..8", "--skip-characters", "-")
+    assert r.returncode == 0 and "Reference offset: 0" in r.stdout and r.stdout.splitlines()[0].startswith("CIGAR: 2=[TS") and r.stdout.splitlines()[0].endswith("]2=")
     r = run(workdir, "align", "-r", "test_files/reference_a.fa", "-q", "test_files/query_a.fa", "--no-ts")
     assert r.returncode == 0 and "CIGAR: " in r.stdout
 
