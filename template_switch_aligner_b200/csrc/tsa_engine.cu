@@ -90,7 +90,8 @@ struct Engine::Impl {
     DevBuf band, winflag;                             // column windows: band vectors of the fill, overflow flags
     bool any_win = false;
     std::vector<int> h_winflag;
-    DevBuf wave_prefix, wave_progress, wave_ticket;   // k_affine_wave: first ticket per pair, progress flag per strip, ticket counter
+    DevBuf wave_prefix, wave_ticket;   // k_affine_wave: first ticket per pair, ticket counter
+    size_t scratch_bytes = 0;
     int wave_tickets = 0;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
     size_t cells = 0, ops_total = 0;
@@ -179,7 +180,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         pm.seq_r = (long long)seq_bytes; seq_bytes += (size_t)pv.n;
         pm.seq_q = (long long)seq_bytes; seq_bytes += (size_t)pv.m;
         pm.vec = (long long)vec; vec += (size_t)pv.n + pv.m + 2;
-        pm.scr = (long long)scr; scr += 3 * ((size_t)pv.n + 1);
+        pm.scr = (long long)scr; scr += (3 * ((size_t)pv.n + 1) + 1) & ~(size_t)1;   // even: k_affine_wave keeps 8-byte entries there
         pm.mat = (long long)cells;
         pm.tab = -1; pm.lw = 0;
         const int W = std::max(pv.n, pv.m) + 1;
@@ -210,7 +211,6 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         }
         I.wave_tickets = prefix.back();
         I.wave_prefix.ensure(prefix.size() * 4);
-        I.wave_progress.ensure((size_t)std::max(1, I.wave_tickets) * 4);
         I.wave_ticket.ensure(4);
         rt::h2d(I.wave_prefix.p, prefix.data(), prefix.size() * 4, I.stream);
         rt::stream_sync(I.stream);   // `prefix` is a local
@@ -239,6 +239,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.tables.ensure(tab);
     I.minvec.ensure(vec * 4);
     I.scratch.ensure(scr * 4);
+    I.scratch_bytes = scr * 4;
     I.best.ensure(n * 4); I.best_layer.ensure(n * 4); I.active.ensure(n * 4); I.next_active.ensure(n * 4);
     I.counters.ensure(64);
     I.thr.ensure(n * 4); I.ub.ensure(n * 4); I.t0.ensure(n * 4); I.resolved.ensure(n * 4);
@@ -535,11 +536,11 @@ void Engine::run_wave() {
         I.dirL[0]->ensure(I.cells);
         I.ck.dir = I.dirL[0]->as<uint8_t>();
     } else I.ck.dir = nullptr;
-    rt::dev_memset(I.wave_progress.p, 0, (size_t)I.wave_tickets * 4, I.stream);
+    rt::dev_memset(I.scratch.p, 0xff, I.scratch_bytes, I.stream);   // boundary entries: tag 7 = "not written"
     rt::dev_memset(I.wave_ticket.p, 0, 4, I.stream);
     WaveArgs wa;
     wa.list = I.d_list_all; wa.n_list = n_all; wa.strip_prefix = I.wave_prefix.as<int>();
-    wa.progress = I.wave_progress.as<int>(); wa.ticket = I.wave_ticket.as<int>();
+    wa.ticket = I.wave_ticket.as<int>();
     const size_t smem = (size_t)WAVE_SMEM_INTS * sizeof(int);
     int blocks = (I.wave_tickets + WAVE_WARPS - 1) / WAVE_WARPS;
 #ifndef TSA_EMUL
@@ -646,6 +647,8 @@ void Engine::fetch_staged(PairCost* out) {
     rt::d2h(I.h_best.data(), I.best.p, n * 4, I.stream);
     rt::d2h(I.h_layer.data(), I.best_layer.p, n * 4, I.stream);
     rt::d2h(I.h_active.data(), I.active.p, n * 4, I.stream);
+    std::vector<int> h_sat;
+    if (!I.ts_enabled) { h_sat.resize(n); rt::d2h(h_sat.data(), I.next_active.p, n * 4, I.stream); }   // k_affine_wave: boundary values saturated
     I.h_winflag.assign(n, 0);
     if (I.any_win && I.ts_enabled) rt::d2h(I.h_winflag.data(), I.winflag.p, n * 4, I.stream);
     rt::stream_sync(I.stream);
@@ -656,6 +659,7 @@ void Engine::fetch_staged(PairCost* out) {
         pc.status = I.status[i];
         if (pc.status != PAIR_OK) continue;
         if (I.h_winflag[i] & 2) { pc.status = PAIR_ERR_TOO_LONG; continue; }   // a column window did not fit the widest class
+        if (!I.ts_enabled && h_sat[i] && I.h_best[i] >= WAVE_SAT) { pc.status = PAIR_ERR_COST_RANGE; continue; }   // exact only below 2^26 - 1
         if (I.h_best[i] >= INF32) { pc.status = PAIR_NO_TARGET; continue; }
         // The jump kernel computes in saturating s16: every path cheaper than INF16 is exact, so a result below
         // INF16 is the optimum; above it a cheaper template-switch path may have been saturated away.

@@ -8,8 +8,14 @@
 //   * inside a strip the warp sweeps anti-diagonals: at step t lane l computes row t - l, so that the left-neighbour
 //     dependency (the insertion state and the diagonal) is the value lane l - 1 produced one step earlier and arrives by
 //     __shfl_up_sync; there is no scan and no dependency inside a step except along the CB cells of a lane;
-//   * strips of one pair are chained through a boundary column in global memory (2 ints per row, written by lane 31,
-//     prefetched 32 rows at a time by the next strip) guarded by a release / acquire progress flag per strip;
+//   * strips of one pair are chained through a boundary column in global memory: one 8-byte entry per row (ND and I of the
+//     strip's last column) written by lane 31 with a single store and prefetched 32 rows at a time, one chunk ahead, by
+//     the next strip.  Every entry carries a 12-bit tag (strip index mod 4095) in the top bits of its two words, so an
+//     entry validates itself: no flag, no fence -- the consumer polls a chunk until all 32 tags are its left neighbour's
+//     (the buffer starts as all ones = tag 4095, which no strip writes, and is reused in place by all strips of the pair:
+//     the latest writer of a row is some earlier strip, and two strips with equal tags are 4095 strips apart, more than
+//     can be in flight).  The two values keep 26 bits: larger finite costs saturate to "infinite" and set a per-pair
+//     flag; a result below 2^26 - 1 is exact regardless (costs are non-negative), anything else is reported as out of range;
 //   * strips are handed out through one atomic ticket in (pair, strip) order, so the strip a warp waits for was always
 //     claimed earlier by a warp that is running: any grid size is deadlock free, long pairs use many warps, short pairs
 //     one.
@@ -38,9 +44,29 @@ struct WaveArgs {
     const int* list;         // pairs of this launch
     int n_list;
     const int* strip_prefix; // [n_list + 1] first ticket of every pair
-    int* progress;           // [tickets] rows of the boundary column published by that strip
     int* ticket;             // next strip to hand out
 };
+
+struct alignas(8) WaveBnd { uint32_t nd, i; };      // boundary entry: values in bits 0..25, tag bits 0-5 in nd[26..31], tag bits 6-11 in i[26..31]
+constexpr int WAVE_SAT = 0x3FFFFFF;                 // 2^26 - 1: boundary values saturate here
+constexpr uint32_t WAVE_TAGS = 4095;
+TSA_DEV WaveBnd wave_bnd_load(const WaveBnd* p) {   // L2 load (another SM wrote it)
+#ifndef TSA_EMUL
+    const unsigned long long v = __ldcg(reinterpret_cast<const unsigned long long*>(p));
+    return WaveBnd{(uint32_t)v, (uint32_t)(v >> 32)};
+#else
+    const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(p);
+    return WaveBnd{q[0], q[1]};
+#endif
+}
+TSA_DEV void wave_bnd_store(WaveBnd* p, WaveBnd v) {
+#ifndef TSA_EMUL
+    __stcg(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v.nd | ((unsigned long long)v.i << 32));
+#else
+    volatile uint32_t* q = reinterpret_cast<volatile uint32_t*>(p);
+    q[0] = v.nd; q[1] = v.i;
+#endif
+}
 
 template <bool TRACE>
 TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_affine_wave(Chunk ck, WaveArgs wa) {
@@ -79,7 +105,8 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
         const uint8_t* Q = ck.seq + pm.seq_q + pm.qo;
         const bool last_strip = s == wave_strips(mm + 1) - 1;
         const int j0 = s * WAVE_SW + lane * CB;
-        int* bnd = ck.scratch + pm.scr;                           // [row][ND, I] of the column left of the next strip
+        WaveBnd* bnd = reinterpret_cast<WaveBnd*>(ck.scratch + pm.scr);   // [row] ND / I of the column left of the next strip
+        const uint32_t tag_in = (uint32_t)(s + WAVE_TAGS - 1) % WAVE_TAGS, tag_out = (uint32_t)s % WAVE_TAGS;   // tags of strip s - 1 / of this strip
         const long long dstride = wave_dir_stride(mm + 1);
         uint8_t* dirp = TRACE ? ck.dir + pm.mat + j0 : nullptr;
 
@@ -97,21 +124,44 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
         }
         int diag_in = INF32;                 // M(i - 1, j0 - 1)
         int out_nd = INF32, out_i = INF32, out_r = 0;            // what lane + 1 needs next step: ND / I of my last column, my row's character
-        int rchunk = 0, bnd_nd = INF32, bnd_i = INF32;
+        int rchunk = 0, bnd_nd = INF32, bnd_i = INF32;          // rows st .. st + 31 (lane k: row st + k)
+        int rnext = 0, nd_next = INF32, i_next = INF32;         // the chunk after that, loaded one chunk ahead
+        auto load_chunk = [&](int first, int& rc_, int& nd_, int& i_) {
+            const int row = first + lane;
+            rc_ = (row >= 1 && row <= nn) ? (int)R[row - 1] : 0;
+            nd_ = INF32; i_ = INF32;
+            if (s > 0 && first <= nn) {
+                for (;;) {
+                    WaveBnd v = WaveBnd{0, 0};
+                    bool ok = true;
+                    if (row <= nn) {
+                        v = wave_bnd_load(bnd + row);
+                        ok = ((v.nd >> 26) | ((v.i >> 26) << 6)) == tag_in;
+                    }
+                    if (ballot(!ok) == 0) {
+                        if (row <= nn) {
+                            nd_ = (int)(v.nd & (uint32_t)WAVE_SAT); i_ = (int)(v.i & (uint32_t)WAVE_SAT);
+                            if (nd_ == WAVE_SAT) nd_ = INF32;
+                            if (i_ == WAVE_SAT) i_ = INF32;
+                        }
+                        break;
+                    }
+                    spin_pause();
+                }
+            }
+        };
+        load_chunk(0, rchunk, bnd_nd, bnd_i);
         int tgt = INF32;
+        bool saturated = false;
         const bool is_root_lane = s == 0 && lane == 0;
         const int tcol = mm - j0;                                  // target column within this lane (0 .. CB-1) or outside
         const int steps = nn + 32;
         for (int st = 0; st < steps; st++) {
             if ((st & 31) == 0) {
-                const int row = st + lane;                        // rows st .. st + 31 enter lane 0 during the next 32 steps
-                rchunk = (row >= 1 && row <= nn) ? (int)R[row - 1] : 0;
-                if (s > 0 && st <= nn) {
-                    const int need = imin(st + 32, nn + 1);
-                    while (ld_acquire_s32(wa.progress + tk - 1) < need) spin_pause();
-                    bnd_nd = row <= nn ? ld_cg_s32(bnd + 2 * row) : INF32;
-                    bnd_i = row <= nn ? ld_cg_s32(bnd + 2 * row + 1) : INF32;
-                }
+                // rows st .. st + 31 enter lane 0 during the next 32 steps; the chunk after them is requested now so that
+                // its latency (and the wait for the strip to the left) overlaps these 32 steps
+                if (st > 0) { rchunk = rnext; bnd_nd = nd_next; bnd_i = i_next; }
+                load_chunk(st + 32, rnext, nd_next, i_next);
             }
             int rch = (int)shfl_up((uint32_t)out_r, 1);
             int lnd = (int)shfl_up((uint32_t)out_nd, 1);
@@ -155,11 +205,12 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
                 out_nd = left_nd; out_i = left_i; out_r = rch;
                 if (TRACE && j0 <= mm) *reinterpret_cast<WaveCodes8*>(dirp + (long long)i * dstride) = WaveCodes8{w0, w1};
                 if (lane == 31 && !last_strip) {
-                    bnd[2 * i] = left_nd; bnd[2 * i + 1] = left_i;
-                    if ((i & 31) == 31 || i == nn) st_release_s32(wa.progress + tk, i + 1);
+                    if ((left_nd >= WAVE_SAT && left_nd < INF32) || (left_i >= WAVE_SAT && left_i < INF32)) saturated = true;
+                    wave_bnd_store(bnd + i, WaveBnd{(uint32_t)imin(left_nd, WAVE_SAT) | ((tag_out & 63u) << 26), (uint32_t)imin(left_i, WAVE_SAT) | ((tag_out >> 6) << 26)});
                 }
             }
         }
+        if (ballot(saturated) != 0 && lane == 0) atomic_or_s32(&ck.next_active[b], 1);   // (next_active is unused without template switches)
         if (last_strip) {
             // every lane's Mup holds row nn now; target: any gap state (context.rs:731-748)
 #pragma unroll
