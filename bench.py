@@ -272,8 +272,19 @@ def run_ours(args):
     jl = max(1, jump_launches)
     achieved = (w_jump * args.steps / jl) / ((jump_ms / jl) * 1e-3) / 1e12 if jump_ms > 0 else None
     peak = s16.value / 1e12
-    roofline = {"bound": "integer (DPX add-min, packed s16x2 lanes)", "kernel": "k_ts_jump<5>", "achieved": achieved, "peak": peak, "unit": "Tadd-min/s",
-                "frac": (achieved / peak) if achieved and peak else None, "traffic": None,
+    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/): bytes per pair of the layer-0 launch,
+    # scaled to the pairs of one launch here; nothing is measured under a profiler in this run
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k_ts_jump5_traffic.json")) as fh:
+            tr = json.load(fh)
+        traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / tr["pairs_in_launch"] * batch
+        traffic_src = tr["source"]
+    except (OSError, KeyError, ValueError):
+        pass
+    roofline = {"bound": "integer (DPX add-min, packed s16x2 lanes)", "kernel": "k_ts_jump<5,false>", "achieved": achieved, "peak": peak, "unit": "Tadd-min/s",
+                "frac": (achieved / peak) if achieved and peak else None, "traffic": traffic, "traffic_unit": "bytes per layer-0 launch (dram read + write)",
+                "traffic_source": traffic_src,
                 "peak_source": "measured in this run by tsa_measure_addmin_peak (back-to-back __viaddmin_s16x2 on all SMs); s32 rate %.2f T/s" % (s32.value / 1e12),
                 "algorithmic_ops_per_launch": w_jump * args.steps / jl, "avg_launch_ms": jump_ms / jl,
                 "kernel_share_of_step": {"jump_ms": jump_ms / args.steps, "fill_ms": fill_ms / args.steps, "step_ms": 1e3 * elapsed / args.steps},
