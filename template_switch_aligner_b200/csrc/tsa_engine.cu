@@ -348,10 +348,12 @@ void Engine::run_staged() {
         }
         int16_t* A = I.PA.as<int16_t>();
         int16_t* B = I.PB.as<int16_t>();
+        // blocks per pair: enough to fill the GPU when the batch is small (1 kb pairs: ~250 blocks each), 16 for read pairs
+        const unsigned gx = (unsigned)std::min<size_t>(1024, std::max<size_t>(16, (cells / std::max<size_t>(1, I.npairs)) / 4096));
         auto step = [&](const int16_t* src, int16_t* dst, int table, int plane, int final_plane, int report) {
             for (int off = 0; off < cnt; off += 65535) {
                 const int c2 = std::min(65535, cnt - off);
-                TSA_LAUNCH(k_flank_step, dim3(16, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, src, dst,
+                TSA_LAUNCH(k_flank_step, dim3(gx, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, src, dst,
                            fd ? fd + (size_t)(plane - 1) * cells : (uint8_t*)nullptr, table, plane, final_plane, report, layer);
                 stats_.launches++;
             }
@@ -360,7 +362,7 @@ void Engine::run_staged() {
         if (layer > 0 && RF > 0) {
             for (int off = 0; off < cnt; off += 65535) {
                 const int c2 = std::min(65535, cnt - off);
-                TSA_LAUNCH(k_seed_to_plane, dim3(16, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, A);
+                TSA_LAUNCH(k_seed_to_plane, dim3(gx, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, A);
                 stats_.launches++;
             }
             for (int s = 1; s <= RF; s++) { step(A, B, 4, s, 0, s < RF ? 1 : 0); std::swap(A, B); }
@@ -461,6 +463,7 @@ void Engine::run_staged() {
     for (int k = 0; k < dev_.n_kinds; k++) { full_mask |= 1u << k; if (dev_.kinds[k].d == 1) rev_mask |= 1u << k; }
     const bool scout = I.opt.scout_round && rev_mask != 0 && rev_mask != full_mask;
     bool capped = false;
+    const unsigned clear_gx = (unsigned)std::min<size_t>(512, std::max<size_t>(8, (I.cells / std::max<size_t>(1, I.npairs)) / 8192));   // blocks per pair
     for (int round = 0; !capped; round++) {
         I.ck.round = round;
         I.ck.kind_mask = (scout && round == 0) ? rev_mask : full_mask;
@@ -475,7 +478,7 @@ void Engine::run_staged() {
             for (int c = 0; c < N_CLASS; c++)
                 for (int off = 0; off < cur_n[c]; off += 65535) {
                     const int cnt = std::min(65535, cur_n[c] - off);
-                    TSA_LAUNCH(k_clear_seeds, dim3(8, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, cur[c] + off, cnt);
+                    TSA_LAUNCH(k_clear_seeds, dim3(clear_gx, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, cur[c] + off, cnt);
                     stats_.launches++;
                 }
             mark(2);
