@@ -5,7 +5,7 @@ from oracle import oracle, tsa_config
 from helpers import parse_config_any
 import parity
 import template_switch_aligner_b200 as tsa
-from template_switch_aligner_b200 import _lib, workloads
+from template_switch_aligner_b200 import _lib, api, workloads
 
 pytestmark = pytest.mark.gpu
 
@@ -258,3 +258,53 @@ def test_column_windows_gpu(lib):
     assert g.status in (0, 9)
     if g.status == 0:
         parity.check_alignment(flat, hard[0], g, "windows hard")
+
+
+def test_single_long_pair_no_ts_gpu(lib):
+    # BASELINE config 5 shape at reduced size (--no-ts).  A 12 kb pair (47 strips, all in flight at once) against the scalar
+    # oracle; a 60 kb pair (235 strips; too large for the oracle's matrices) through size-independent properties: the alignment
+    # rescoring to the cost, symmetry under swapping the sequences (the sample model is symmetric), and additivity when the
+    # pair is cut at a match of the returned alignment (two ranged alignments of the same pair).
+    text = workloads.sample_config_text()
+    flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+    nots = tsa.Aligner(costs=text, no_ts=True, lib=lib)
+    r, q = workloads.long_pair(5, 12000, sub_rate=0.012, indel_rate=0.003)
+    parity.check_batch(nots, flat, [(r, q), (r, q, (1234, len(r) - 77, 999, len(q) - 5))], no_ts=True, label="wave12k")
+    r, q = workloads.long_pair(6, 60000, sub_rate=0.012, indel_rate=0.003)
+    whole, swapped = nots.align_batch([(r, q), (q, r)])
+    assert whole.found and swapped.found and whole.cost == swapped.cost
+    parity.check_alignment(flat, (r, q), whole, "wave60k")
+    # walk to the first match at or after the middle of the reference
+    i = j = 0
+    cut = None
+    for count, t, *_ in whole.ops:
+        for _ in range(count):
+            if t == 3 and i >= len(r) // 2 and cut is None:
+                cut = (i, j)
+            i += t in (1, 2, 3)
+            j += t in (0, 2, 3)
+    assert cut is not None
+    left, right = nots.align_batch([(r, q, (0, cut[0], 0, cut[1])), (r, q, (cut[0], len(r), cut[1], len(q)))])
+    assert left.found and right.found and left.cost + right.cost == whole.cost
+
+
+def test_postprocess_through_the_abi_gpu(lib):
+    # tsa_options.postprocess on the GPU path == the host-only entry applied to the searched alignment; with the extension the
+    # reported range grows over the matching flanks of a ranged pair and the cost does not change
+    text = workloads.sample_config_text()
+    pairs = workloads.read_pairs(64, start=700)
+    ranged = [(r, q, (10, len(r) - 10, 10, len(q) - 10)) for r, q in pairs[:16] if r[:10] == q[:10]]
+    plain = tsa.Aligner(costs=text, lib=lib)
+    post = tsa.Aligner(costs=text, postprocess=api.POST_EXTEND_BEYOND_RANGE | api.POST_EQUAL_COST_RANGES, lib=lib)
+    a = plain.align_batch(pairs + ranged)
+    b = post.align_batch(pairs + ranged)
+    n_ranges = 0
+    for p, x, y in zip(pairs + ranged, a, b):
+        assert x.found and y.found
+        ops, ranges, rng, cost = api.postprocess(plain.config, p[0], p[1], x.ops, x.range, api.POST_EXTEND_BEYOND_RANGE | api.POST_EQUAL_COST_RANGES)
+        assert (ops, ranges, rng) == (y.ops, y.equal_cost_ranges, y.range)
+        assert cost <= x.cost and y.cost == x.cost
+        n_ranges += sum(e is not None for e in y.equal_cost_ranges)
+        if len(p) > 2:
+            assert y.range[0] < p[2][0] or p[0][p[2][0] - 1] != p[1][p[2][2] - 1]
+    assert n_ranges >= 32
