@@ -29,6 +29,17 @@ struct DevBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+// Page-locked host staging buffer: device-to-host copies of results run at PCIe speed instead of through a bounce buffer.
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes > cap) { rt::host_free(p); p = rt::host_alloc(bytes); cap = bytes; }
+    }
+    ~HostBuf() { rt::host_free(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
 size_t jump_smem_per_warp(int A, int C) {
     const int LW = 32 * C;
     int KL = 0;
@@ -111,6 +122,7 @@ struct Engine::Impl {
     Chunk ck = Chunk();
     bool ts_enabled = false;
     std::vector<int> h_best, h_layer, h_active;
+    HostBuf h_ops, h_recs, h_small;      // pinned staging of the traceback output
 #ifndef TSA_EMUL
     cudaEvent_t ev[4];
 #endif
@@ -673,24 +685,26 @@ void Engine::fetch_staged(PairCost* out) {
         pc.layers = I.h_layer[i];
     }
     if (!I.opt.traceback) return;
-    std::vector<int> len(n), nrec(n), tst(n);
-    std::vector<uint8_t> ops(I.ops_total);
-    std::vector<TsRecord> recs(n * (size_t)I.max_recs);
-    rt::d2h(len.data(), I.ops_len.p, n * 4, I.stream);
-    rt::d2h(nrec.data(), I.n_recs.p, n * 4, I.stream);
-    rt::d2h(tst.data(), I.tstatus.p, n * 4, I.stream);
-    rt::d2h(ops.data(), I.ops.p, I.ops_total, I.stream);
-    rt::d2h(recs.data(), I.recs.p, recs.size() * sizeof(TsRecord), I.stream);
+    const size_t n_recs_total = n * (size_t)I.max_recs;
+    I.h_small.ensure(n * 12); I.h_ops.ensure(I.ops_total); I.h_recs.ensure(n_recs_total * sizeof(TsRecord));
+    int* len = I.h_small.as<int>(); int* nrec = len + n; int* tst = nrec + n;
+    uint8_t* ops = I.h_ops.as<uint8_t>();
+    TsRecord* recs = I.h_recs.as<TsRecord>();
+    rt::d2h(len, I.ops_len.p, n * 4, I.stream);
+    rt::d2h(nrec, I.n_recs.p, n * 4, I.stream);
+    rt::d2h(tst, I.tstatus.p, n * 4, I.stream);
+    rt::d2h(ops, I.ops.p, I.ops_total, I.stream);
+    rt::d2h(recs, I.recs.p, n_recs_total * sizeof(TsRecord), I.stream);
     rt::stream_sync(I.stream);
-    stats_.d2h_bytes += (long long)(n * 12 + I.ops_total + recs.size() * sizeof(TsRecord));
+    stats_.d2h_bytes += (long long)(n * 12 + I.ops_total + n_recs_total * sizeof(TsRecord));
     for (size_t i = 0; i < n; i++) {
         PairCost& pc = out[i];
         if (pc.status != PAIR_OK) continue;
         pc.trace_status = tst[i];
         if (tst[i] != TRACE_OK) continue;
-        const uint8_t* src = ops.data() + I.h_ops_off[i];
+        const uint8_t* src = ops + I.h_ops_off[i];
         pc.ops.assign(std::reverse_iterator<const uint8_t*>(src + len[i]), std::reverse_iterator<const uint8_t*>(src));
-        const TsRecord* rs = recs.data() + i * (size_t)I.max_recs;
+        const TsRecord* rs = recs + i * (size_t)I.max_recs;
         pc.recs.assign(std::reverse_iterator<const TsRecord*>(rs + nrec[i]), std::reverse_iterator<const TsRecord*>(rs));
     }
 }
@@ -700,6 +714,12 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
     size_t i = 0;
     EngineStats total;
     size_t budget = opt.chunk_bytes;
+    if (budget == 0) {
+        // small jobs fit anyway: ask the driver for the free memory (a slow call) only when it matters
+        size_t rough = 0;
+        for (size_t k = 0; k < n && rough <= ((size_t)32 << 30); k++) rough += (size_t)(pairs[k].n + 1) * (pairs[k].m + 1) * 40 + 4096;
+        if (rough <= ((size_t)32 << 30)) budget = (size_t)64 << 30;
+    }
     if (budget == 0) {
 #ifndef TSA_EMUL
         size_t free_b = 0, total_b = 0;
