@@ -125,32 +125,33 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
         int diag_in = INF32;                 // M(i - 1, j0 - 1)
         int out_nd = INF32, out_i = INF32, out_r = 0;            // what lane + 1 needs next step: ND / I of my last column, my row's character
         int rchunk = 0, bnd_nd = INF32, bnd_i = INF32;          // rows st .. st + 31 (lane k: row st + k)
-        int rnext = 0, nd_next = INF32, i_next = INF32;         // the chunk after that, loaded one chunk ahead
-        auto load_chunk = [&](int first, int& rc_, int& nd_, int& i_) {
+        int rnext = 0;                                          // the chunk after that: characters and raw boundary entries,
+        WaveBnd raw_next = WaveBnd{0, 0};                       // requested one chunk ahead and validated when they are needed
+        // request: no wait -- the entries may not be written yet, the tags tell at validation time
+        auto request_chunk = [&](int first) {
             const int row = first + lane;
-            rc_ = (row >= 1 && row <= nn) ? (int)R[row - 1] : 0;
-            nd_ = INF32; i_ = INF32;
+            rnext = (row >= 1 && row <= nn) ? (int)R[row - 1] : 0;
+            if (s > 0 && row <= nn) raw_next = wave_bnd_load(bnd + row);
+        };
+        // validate: all 32 tags must be the left neighbour's; entries that were requested too early are read again
+        auto accept_chunk = [&](int first) {
+            const int row = first + lane;
+            rchunk = rnext; bnd_nd = INF32; bnd_i = INF32;
             if (s > 0 && first <= nn) {
                 for (;;) {
-                    WaveBnd v = WaveBnd{0, 0};
-                    bool ok = true;
-                    if (row <= nn) {
-                        v = wave_bnd_load(bnd + row);
-                        ok = ((v.nd >> 26) | ((v.i >> 26) << 6)) == tag_in;
-                    }
-                    if (ballot(!ok) == 0) {
-                        if (row <= nn) {
-                            nd_ = (int)(v.nd & (uint32_t)WAVE_SAT); i_ = (int)(v.i & (uint32_t)WAVE_SAT);
-                            if (nd_ == WAVE_SAT) nd_ = INF32;
-                            if (i_ == WAVE_SAT) i_ = INF32;
-                        }
-                        break;
-                    }
+                    const bool ok = row > nn || ((raw_next.nd >> 26) | ((raw_next.i >> 26) << 6)) == tag_in;
+                    if (ballot(!ok) == 0) break;
                     spin_pause();
+                    if (row <= nn) raw_next = wave_bnd_load(bnd + row);
+                }
+                if (row <= nn) {
+                    bnd_nd = (int)(raw_next.nd & (uint32_t)WAVE_SAT); bnd_i = (int)(raw_next.i & (uint32_t)WAVE_SAT);
+                    if (bnd_nd == WAVE_SAT) bnd_nd = INF32;
+                    if (bnd_i == WAVE_SAT) bnd_i = INF32;
                 }
             }
         };
-        load_chunk(0, rchunk, bnd_nd, bnd_i);
+        request_chunk(0);
         int tgt = INF32;
         bool saturated = false;
         const bool is_root_lane = s == 0 && lane == 0;
@@ -158,10 +159,11 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
         const int steps = nn + 32;
         for (int st = 0; st < steps; st++) {
             if ((st & 31) == 0) {
-                // rows st .. st + 31 enter lane 0 during the next 32 steps; the chunk after them is requested now so that
-                // its latency (and the wait for the strip to the left) overlaps these 32 steps
-                if (st > 0) { rchunk = rnext; bnd_nd = nd_next; bnd_i = i_next; }
-                load_chunk(st + 32, rnext, nd_next, i_next);
+                // rows st .. st + 31 enter lane 0 during the next 32 steps: validate their entries (requested 32 steps ago), then
+                // request the chunk after them, so that the load latency overlaps these 32 steps.  A strip that runs too
+                // close behind its left neighbour reads again here and thereby falls back until its requests succeed.
+                accept_chunk(st);
+                request_chunk(st + 32);
             }
             int rch = (int)shfl_up((uint32_t)out_r, 1);
             int lnd = (int)shfl_up((uint32_t)out_nd, 1);
