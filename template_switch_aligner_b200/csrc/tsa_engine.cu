@@ -106,7 +106,7 @@ struct Engine::Impl {
     int wave_tickets = 0;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
     size_t cells = 0, ops_total = 0;
-    int max_m = 0;                       // longest query of the staged chunk (column count of the primary fill)
+    int max_m = 0, max_n = 0;            // longest query / reference of the staged chunk
     int max_recs = 0;
     DevBuf cfg, lc, meta, seq, D, DT, seedA, seedB, minvec, scratch, best, best_layer, active, next_active, counters, lists, thr, ub, t0, resolved;
     std::vector<PairMeta> metas;
@@ -183,11 +183,11 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     for (auto& l : I.class_list) l.clear();
     for (auto& v : I.class_maxlen) v = 0;
     size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0, tab = 0;
-    I.max_m = 0;
+    I.max_m = 0; I.max_n = 0;
     for (size_t i = 0; i < n; i++) {
         const PairView& pv = pairs[i];
         PairMeta& pm = I.metas[i];
-        I.max_m = std::max(I.max_m, pv.m);
+        I.max_m = std::max(I.max_m, pv.m); I.max_n = std::max(I.max_n, pv.n);
         pm.n = pv.n; pm.m = pv.m; pm.ro = pv.ro; pm.rl = pv.rl; pm.qo = pv.qo; pm.ql = pv.ql;
         pm.seq_r = (long long)seq_bytes; seq_bytes += (size_t)pv.n;
         pm.seq_q = (long long)seq_bytes; seq_bytes += (size_t)pv.m;
@@ -362,12 +362,22 @@ void Engine::run_staged() {
         int16_t* B = I.PB.as<int16_t>();
         // blocks per pair: enough to fill the GPU when the batch is small (1 kb pairs: ~250 blocks each), 16 for read pairs
         const unsigned gx = (unsigned)std::min<size_t>(1024, std::max<size_t>(16, (cells / std::max<size_t>(1, I.npairs)) / 4096));
-        auto step = [&](const int16_t* src, int16_t* dst, int table, int plane, int final_plane, int report) {
-            for (int off = 0; off < cnt; off += 65535) {
-                const int c2 = std::min(65535, cnt - off);
-                TSA_LAUNCH(k_flank_step, dim3(gx, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, src, dst,
-                           fd ? fd + (size_t)(plane - 1) * cells : (uint8_t*)nullptr, table, plane, final_plane, report, layer);
-                stats_.launches++;
+        // `count` flank moves from plane `plane0` (in *src) in launches of up to FLANK_FS moves; the result ends up in *src
+        const int tiles_x = (I.max_m + 1 + FLANK_FT - 1) / FLANK_FT, tiles_y = (I.max_n + 1 + FLANK_FT - 1) / FLANK_FT;
+        auto run = [&](int16_t*& src, int16_t*& dst, int table, int plane0, int count, int final_at_end, int no_report_plane) {
+#ifndef TSA_EMUL
+            static bool attr_set = false;
+            if (!attr_set) { rt::check(cudaFuncSetAttribute(k_flank_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLANK_SMEM), "cudaFuncSetAttribute"); attr_set = true; }
+#endif
+            for (int done = 0; done < count; done += FLANK_FS) {
+                const int ns = std::min(FLANK_FS, count - done);
+                for (int off = 0; off < cnt; off += 65535) {
+                    const int c2 = std::min(65535, cnt - off);
+                    TSA_LAUNCH(k_flank_fused, dim3((unsigned)(tiles_x * tiles_y), (unsigned)c2), dim3(256), FLANK_SMEM, I.stream, I.ck, d_list + off, c2, src, dst, fd, table,
+                               plane0 + done, ns, (final_at_end && done + ns == count) ? 1 : 0, no_report_plane, layer, tiles_x);
+                    stats_.launches++;
+                }
+                std::swap(src, dst);
             }
         };
         I.ck.pl_in = nullptr;
@@ -377,7 +387,7 @@ void Engine::run_staged() {
                 TSA_LAUNCH(k_seed_to_plane, dim3(gx, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, A);
                 stats_.launches++;
             }
-            for (int s = 1; s <= RF; s++) { step(A, B, 4, s, 0, s < RF ? 1 : 0); std::swap(A, B); }
+            run(A, B, 4, 0, RF, 0, RF);   // the target in plane RF is reported by the primary fill
             I.ck.pl_in = A;
         }
         I.ck.pl_out = LF > 0 ? B : nullptr;
@@ -389,12 +399,9 @@ void Engine::run_staged() {
                 TSA_LAUNCH(k_reset_minvec, dim3(4, (unsigned)c2), dim3(256), 0, I.stream, I.ck, d_list + off, c2, layer);
                 stats_.launches++;
             }
-            const int16_t* src = B;
+            int16_t* src = B;
             int16_t* dst = A;
-            for (int s = 1; s <= LF; s++) {
-                step(src, dst, 3, RF + s, s == LF ? 1 : 0, 1);
-                int16_t* t = const_cast<int16_t*>(src); src = dst; dst = t;
-            }
+            run(src, dst, 3, RF, LF, 1, -1);
         }
         TSA_LAUNCH(k_layer_finish, dim3((unsigned)((cnt + 255) / 256)), dim3(256), 0, I.stream, I.ck, d_list, cnt, layer);
         stats_.launches++;

@@ -131,3 +131,18 @@ def test_column_windows_emulated():
     wide = tsa.Aligner(costs=base, alphabet="dna-n", dev_flags=4, lib=emul())
     res = wide.align_batch(workloads.read_pairs(1, start=500, length=200))[0]
     assert res.status == 9 and "windows" in res.message
+
+
+def test_flank_tiles_emulated():
+    # k_flank_fused: pairs longer than one 64 x 64 tile (halo exchange through the planes in global memory) and flank lengths
+    # above the 8 planes of one launch; costs against the oracle, alignments walked through the per-plane codes
+    from template_switch_aligner_b200 import workloads
+    from oracle import tsa_config
+    base = workloads.sample_config_text()
+    for lf, rf, length, count in ((5, 5, 100, 2), (12, 9, 140, 1)):
+        text = base.replace("left_flank_length = 0", f"left_flank_length = {lf}").replace("right_flank_length = 0", f"right_flank_length = {rf}")
+        flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+        pairs = workloads.read_pairs(count, start=40, length=length)
+        pairs.append((pairs[0][0], pairs[0][1], (3, length - 2, 5, len(pairs[0][1]))))
+        n_ts = parity.check_batch(tsa.Aligner(costs=text, lib=emul()), flat, pairs, label=f"flank tiles {lf}/{rf}")
+        assert n_ts >= 1
