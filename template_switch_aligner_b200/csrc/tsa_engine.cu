@@ -319,7 +319,7 @@ void Engine::run_staged() {
     stats_.jump_ms = stats_.fill_ms = 0;
     const int n_all = (int)I.list_all.size();
     if (n_all == 0) return;
-    const size_t k1_smem = (size_t)K1_WARPS * MAX_ALPHABET * MAX_ALPHABET * sizeof(int);
+    const size_t k1_smem = (size_t)K1_WARPS * K1_SMEM_INTS * sizeof(int);
     rt::dev_memset(I.active.p, 0, I.npairs * 4, I.stream);
     rt::dev_memset(I.next_active.p, 0, I.npairs * 4, I.stream);
     if (!I.ts_enabled) { run_wave(); run_trace(); return; }
