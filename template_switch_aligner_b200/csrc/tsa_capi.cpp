@@ -141,7 +141,7 @@ void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
         break;
     case PAIR_NO_TARGET: r.status = TSA_OK; r.result_type = TSA_NO_TARGET; break;
     case PAIR_ERR_TOO_LONG: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "template-switch column windows exceed 1056 columns at this cost threshold"); break;
-    case PAIR_ERR_COST_RANGE: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "alignment cost exceeds the integer range of the kernels (2^14 with template switches, 2^26 without)"); break;
+    case PAIR_ERR_COST_RANGE: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "alignment cost exceeds the kernels' integer range (2^14 with template switches, else 2^26)"); break;
     case PAIR_ERR_LAYER_CAP: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "more template switches than max_template_switches still improve the cost"); break;
     case PAIR_ERR_FLANKS: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "flank lengths above 255 are not supported"); break;
     default: r.status = TSA_ERR_ARGUMENT; break;

@@ -308,3 +308,24 @@ def test_postprocess_through_the_abi_gpu(lib):
         if len(p) > 2:
             assert y.range[0] < p[2][0] or p[0][p[2][0] - 1] != p[1][p[2][2] - 1]
     assert n_ranges >= 32
+
+
+def test_no_ts_random_models_long_gpu(lib):
+    # k_affine_wave under random cost models (asymmetric tables, infinite entries, N characters), pairs of several strips with
+    # random ranges: optimum against the scalar oracle, alignments rescored
+    import random
+    import randcfg
+    from helpers import config_to_text
+    checked = 0
+    for seed in range(300, 312):
+        rng = random.Random(seed)
+        cfg = randcfg.random_config(rng)
+        flat = oracle.FlatConfig(cfg)
+        cases = []
+        for k in range(4):
+            r, q = randcfg.random_pair(rng, max_len=rng.choice([300, 520, 900]), n_weight=0.02)
+            cases.append((r, q, randcfg.random_range(rng, r, q)))
+        aligner = tsa.Aligner(costs=config_to_text(cfg), no_ts=True, lib=lib)
+        parity.check_batch(aligner, flat, cases, no_ts=True, label=f"wave seed {seed}")
+        checked += len(cases)
+    assert checked == 48
