@@ -181,7 +181,13 @@ void postprocess_result(const HostConfig& cfg, const PairView& pv, int32_t flags
 // Result assembly (run-length encoding, post-processing) of a batch on the host cores.
 template <class F>
 void parallel_for(size_t n, F&& body) {
-    const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    // host threads of this process: TSA_B200_THREADS, else the cores divided among the ranks of a torchrun launch
+    static const size_t hw = []() -> size_t {
+        size_t cores = std::max<size_t>(1, std::thread::hardware_concurrency());
+        if (const char* t = getenv("TSA_B200_THREADS")) { const long v = atol(t); if (v > 0) return (size_t)v; }
+        if (const char* w = getenv("LOCAL_WORLD_SIZE")) { const long v = atol(w); if (v > 1) cores = std::max<size_t>(1, cores / (size_t)v); }
+        return cores;
+    }();
     const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), (n + 255) / 256);
     if (nt <= 1) { for (size_t i = 0; i < n; i++) body(i); return; }
     std::vector<std::thread> th;
