@@ -2,6 +2,7 @@
 #include "tsalign_b200.h"
 
 #include <chrono>
+#include <exception>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -23,6 +24,7 @@ struct tsa_config {
     HostConfig host;
     std::mutex lock;
     std::unique_ptr<Engine> engine[16];
+    std::unique_ptr<Engine> engine2[16];   // second engine (own stream and buffers) for the other half of a large batch
 };
 
 namespace {
@@ -373,7 +375,32 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     encode_pairs(cfg->host, pairs, n, enc);
     auto t1 = std::chrono::steady_clock::now();
     std::vector<PairCost> costs(enc.views.size());
-    engine.align_costs(enc.views.data(), enc.views.size(), engine_options(o), costs.data());
+    const size_t live = enc.views.size();
+#ifndef TSA_EMUL
+    const bool split = live >= 4096 && !o.no_ts;
+#else
+    const bool split = false;   // the emulator is single-threaded
+#endif
+    if (split) {
+        // Two halves on two engines (two streams, two sets of buffers) driven by two host threads: staging, result copies and
+        // the latency-bound tails of one half overlap the kernels of the other.
+        if (!mcfg->engine2[slot] || !mcfg->engine2[slot]->ok()) mcfg->engine2[slot].reset(new Engine(cfg->host, o.device));
+        Engine& second = *mcfg->engine2[slot];
+        if (!second.ok()) { set_err(err, errcap, second.error()); mcfg->engine2[slot].reset(); return TSA_ERR_NO_DEVICE; }
+        const size_t half = live / 2;
+        const AlignOptions ao = engine_options(o);
+        std::exception_ptr failed;
+        std::thread other([&]() {
+            try { second.align_costs(enc.views.data() + half, live - half, ao, costs.data() + half); }
+            catch (...) { failed = std::current_exception(); }
+        });
+        try { engine.align_costs(enc.views.data(), half, ao, costs.data()); }
+        catch (...) { other.join(); throw; }
+        other.join();
+        if (failed) std::rethrow_exception(failed);
+    } else {
+        engine.align_costs(enc.views.data(), live, engine_options(o), costs.data());
+    }
     auto t2 = std::chrono::steady_clock::now();
     for (size_t i = 0; i < n; i++) {
         memset(&out[i], 0, sizeof(tsa_result));
@@ -396,7 +423,7 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     return TSA_OK;
 } catch (const std::exception& e) {
     // e.g. cudaMalloc failure: drop the cached engine (its buffers) and report; nothing is thrown across the ABI
-    if (cfg) { tsa_config* mcfg = const_cast<tsa_config*>(cfg); std::lock_guard<std::mutex> guard(mcfg->lock); for (auto& en : mcfg->engine) en.reset(); }
+    if (cfg) { tsa_config* mcfg = const_cast<tsa_config*>(cfg); std::lock_guard<std::mutex> guard(mcfg->lock); for (auto& en : mcfg->engine) en.reset(); for (auto& en : mcfg->engine2) en.reset(); }
     set_err(err, errcap, e.what());
     return TSA_ERR_INTERNAL;
 }

@@ -3,6 +3,7 @@
 #include "tsa_engine.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 
@@ -62,7 +63,7 @@ void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len
     const int warps = jump_warps(A, C);
     const size_t smem = jump_smem_per_warp(A, C) * warps;
 #ifndef TSA_EMUL
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set(false);
     if (!attr_set) {
         rt::check(cudaFuncSetAttribute(k_ts_jump<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
         rt::check(cudaFuncSetAttribute(k_ts_jump<C, WIN>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
@@ -366,7 +367,7 @@ void Engine::run_staged() {
         const int tiles_x = (I.max_m + 1 + FLANK_FT - 1) / FLANK_FT, tiles_y = (I.max_n + 1 + FLANK_FT - 1) / FLANK_FT;
         auto run = [&](int16_t*& src, int16_t*& dst, int table, int plane0, int count, int final_at_end, int no_report_plane) {
 #ifndef TSA_EMUL
-            static bool attr_set = false;
+            static std::atomic<bool> attr_set(false);
             if (!attr_set) { rt::check(cudaFuncSetAttribute(k_flank_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLANK_SMEM), "cudaFuncSetAttribute"); attr_set = true; }
 #endif
             for (int done = 0; done < count; done += FLANK_FS) {
@@ -566,7 +567,7 @@ void Engine::run_wave() {
     const size_t smem = (size_t)WAVE_SMEM_INTS * sizeof(int);
     int blocks = (I.wave_tickets + WAVE_WARPS - 1) / WAVE_WARPS;
 #ifndef TSA_EMUL
-    static int resident = 0;
+    static std::atomic<int> resident(0);
     if (!resident) {
         cudaDeviceProp prop;
         rt::check(cudaGetDeviceProperties(&prop, I.device), "cudaGetDeviceProperties");
@@ -579,7 +580,7 @@ void Engine::run_wave() {
             fprintf(stderr, "[tsalign_b200] k_affine_wave: %d / %d regs (trace / costs), %d blocks/SM resident\n", fa.numRegs, fb.numRegs, per_sm);
         }
     }
-    blocks = std::min(blocks, resident);   // persistent: every warp takes strips from the ticket until none is left
+    blocks = std::min(blocks, resident.load());   // persistent: every warp takes strips from the ticket until none is left
     rt::check(cudaEventRecord(I.ev[0], I.stream), "cudaEventRecord");
 #else
     blocks = std::min(blocks, 2);
@@ -602,7 +603,7 @@ static void launch_trace(const Chunk& ck, const TraceLayers& tl, TraceOut to, De
     const int warps = jump_warps(A, C);
     const size_t smem = jump_smem_per_warp(A, C) * warps;
 #ifndef TSA_EMUL
-    static bool attr_set = false;
+    static std::atomic<bool> attr_set(false);
     if (!attr_set) {
         rt::check(cudaFuncSetAttribute(k_traceback<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
         attr_set = true;
