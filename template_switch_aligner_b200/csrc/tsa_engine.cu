@@ -725,7 +725,8 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
     if (budget == 0) {
         // small jobs fit anyway: ask the driver for the free memory (a slow call) only when it matters
         size_t rough = 0;
-        for (size_t k = 0; k < n && rough <= ((size_t)32 << 30); k++) rough += (size_t)(pairs[k].n + 1) * (pairs[k].m + 1) * 40 + 4096;
+        const size_t per_cell = 40 + (size_t)(dev_.left_flank + dev_.right_flank) * 8;
+        for (size_t k = 0; k < n && rough <= ((size_t)32 << 30); k++) rough += (size_t)(pairs[k].n + 1) * (pairs[k].m + 1) * per_cell + 4096;
         if (rough <= ((size_t)32 << 30)) budget = (size_t)64 << 30;
     }
     if (budget == 0) {
@@ -733,7 +734,7 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
         size_t free_b = 0, total_b = 0;
         rt::check(cudaSetDevice(impl_->device), "cudaSetDevice");
         rt::check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
-        budget = std::max<size_t>((size_t)1 << 30, free_b / 2);
+        budget = std::max<size_t>((size_t)1 << 30, free_b / 3);   // a second engine may be working on the other half of the batch
 #else
         budget = (size_t)1 << 30;
 #endif
@@ -744,6 +745,8 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
             const size_t cells = (size_t)(pairs[j].n + 1) * (pairs[j].m + 1);
             size_t b = (!opt.no_ts && dev_.n_kinds > 0) ? bytes_per_pair(pairs[j].n, pairs[j].m) : (size_t)(pairs[j].n + pairs[j].m) * 20 + 512;
             if (opt.traceback) b += cells * ((!opt.no_ts && dev_.n_kinds > 0) ? 9 : 1) + 3 * (size_t)(pairs[j].n + pairs[j].m) + 256;   // codes (+ D) of ~3 layers, ops
+            if (!opt.no_ts && dev_.n_kinds > 0 && (dev_.left_flank > 0 || dev_.right_flank > 0))   // flank planes, and their codes of ~4 layers
+                b += cells * (12 + (opt.traceback ? (size_t)(dev_.left_flank + dev_.right_flank + 1) * 4 : 0));
             if (j > i && bytes + b > budget) break;
             bytes += b; j++;
         }
