@@ -67,8 +67,18 @@ typedef struct {
     int32_t no_traceback;          /* 1 = costs only (ops == NULL) */
     int32_t reserved;
     int32_t postprocess;           /* TSA_POST_* bits: what template_switch_distance_a_star_align does after the search (a_star_aligner.rs:238-253) */
+    int32_t flags;                 /* TSA_FLAG_* bits */
+    int32_t total_length_strategy; /* --ts-total-length-strategy (align.rs:112-118): 0 = maximise (the reference's default), 1 = none */
+    int32_t descendant_strategy;   /* --ts-descendant-strategy (strategies/descendant.rs:22-104): 0 = any, 1 = allow-only-all-equal */
+    int32_t force_label_correcting;/* --force-label-correcting (align.rs:119-122): accepted; a dense fill is exact either way */
     int32_t reserved2;
 } tsa_options;
+
+/* tsa_options.flags */
+enum {
+    TSA_FLAG_KEEP_FLANK_RUNS = 1   /* do not merge flank and non-flank variants of a primary operation into one run (the reference merges them,
+                                      alignment_type.rs:101-121, which loses where a flank begins): lets a checker rescore flank alignments */
+};
 
 /* tsa_options.postprocess (host work per found alignment, O(length^2) like the reference's) */
 enum {

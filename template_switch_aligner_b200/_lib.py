@@ -36,7 +36,8 @@ EXPORTS = [
 class TsaOptions(C.Structure):
     _fields_ = [("no_ts", C.c_int32), ("device", C.c_int32), ("cost_limit", C.c_uint64), ("memory_limit", C.c_uint64),
                 ("max_template_switches", C.c_int32), ("first_threshold", C.c_int32), ("no_traceback", C.c_int32), ("reserved", C.c_int32),
-                ("postprocess", C.c_int32), ("reserved2", C.c_int32)]
+                ("postprocess", C.c_int32), ("flags", C.c_int32), ("total_length_strategy", C.c_int32), ("descendant_strategy", C.c_int32),
+                ("force_label_correcting", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class TsaPair(C.Structure):
@@ -114,10 +115,6 @@ def default():
     """The product library.  Raises if it has not been built -- there is nothing to fall back to."""
     global _DEFAULT
     if _DEFAULT is None:
-        alt = os.environ.get("TSALIGN_B200_LIB")   # developer knob: an alternative build of the same CUDA library
-        if alt:
-            _DEFAULT = bind(C.CDLL(alt))
-            return _DEFAULT
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()' "

@@ -106,7 +106,8 @@ def _make_pairs(pairs: Sequence[tuple]):
     return arr, keep
 
 
-def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0, traceback=True, scout=False, dev_flags=0, postprocess=0) -> TsaOptions:
+def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_template_switches=0, first_threshold=0, traceback=True, scout=False, dev_flags=0, postprocess=0,
+             flags=0, total_length_strategy="maximise", descendant_strategy="any", force_label_correcting=False) -> TsaOptions:
     o = TsaOptions()
     o.no_ts = int(bool(no_ts))
     o.device = device
@@ -117,11 +118,16 @@ def _options(no_ts=False, device=0, cost_limit=None, memory_limit=None, max_temp
     o.no_traceback = 0 if traceback else 1
     o.reserved = (1 if scout else 0) | (dev_flags & ~1)   # developer knobs of the engine (tsa_capi.cpp: engine_options)
     o.postprocess = int(postprocess)
+    o.flags = int(flags)
+    o.total_length_strategy = {"maximise": 0, "none": 1}[total_length_strategy]
+    o.descendant_strategy = {"any": 0, "allow-only-all-equal": 1}[descendant_strategy]
+    o.force_label_correcting = int(bool(force_label_correcting))
     return o
 
 
 _OP_STRUCT = struct.Struct("<qiiiiqbbbbi")  # tsa_op: count, type, primary, secondary, direction, value, equal-cost range, reserved
 POST_EXTEND_BEYOND_RANGE, POST_EQUAL_COST_RANGES = 1, 2   # TSA_POST_* of include/tsalign_b200.h
+FLAG_KEEP_FLANK_RUNS = 1                                   # TSA_FLAG_* of include/tsalign_b200.h
 
 
 class BatchResult:
@@ -305,7 +311,8 @@ class Aligner:
                  total_length_strategy: str = "maximise", costs: Optional[str] = None,
                  costs_file: Optional[Union[str, pathlib.Path]] = None, alphabet: str = "dna-n", device: int = 0,
                  first_threshold: int = 0, traceback: bool = True, scout: bool = False, dev_flags: int = 0,
-                 postprocess: Optional[int] = None, lib=None) -> None:
+                 postprocess: Optional[int] = None, flags: int = 0, descendant_strategy: str = "any",
+                 force_label_correcting: bool = False, max_template_switches: int = 0, lib=None) -> None:
         if costs is not None and costs_file is not None:
             raise ValueError("Provide at most one of 'costs' or 'costs_file'.")
         if min_length_strategy not in _MIN_LENGTH:
@@ -325,9 +332,20 @@ class Aligner:
         # beyond the range and computes equal-cost ranges (python_bindings/src/lib.rs:124-133), align_batch() returns the
         # searched alignments as they are; an int (POST_* bits) applies to both
         self.postprocess = postprocess
+        self.flags = int(flags)                 # FLAG_* bits
+        self.total_length_strategy = total_length_strategy
+        if descendant_strategy not in ("any", "allow-only-all-equal"):
+            raise ValueError(f"unknown descendant_strategy {descendant_strategy!r}")
+        self.descendant_strategy = descendant_strategy
+        self.force_label_correcting = bool(force_label_correcting)
+        self.max_template_switches = int(max_template_switches)
         self.dev_flags = int(dev_flags)         # developer knobs (2: no column windows for medium pairs; 4: small windows, emulator only)
         self.first_threshold = first_threshold  # tuning of the exact pruning only; results do not depend on it
         self.config = Config(costs, alphabet, lib=self._lib)
+
+    def _strategy_kwargs(self):
+        return dict(flags=self.flags, total_length_strategy=self.total_length_strategy, descendant_strategy=self.descendant_strategy,
+                    force_label_correcting=self.force_label_correcting, max_template_switches=self.max_template_switches)
 
     # -- batch entry point: the call the GPU path is built for ----------------------------------------------
     def align_batch(self, pairs: Sequence[tuple], *, cost_limit: Optional[int] = None, memory_limit: Optional[int] = None,
@@ -338,7 +356,7 @@ class Aligner:
         err = C.create_string_buffer(512)
         post = postprocess if postprocess is not None else (self.postprocess or 0)
         opt = _options(self.no_ts, self.device, cost_limit, memory_limit, first_threshold=self.first_threshold, traceback=self.traceback, scout=self.scout,
-                       dev_flags=self.dev_flags, postprocess=post)
+                       dev_flags=self.dev_flags, postprocess=post, **self._strategy_kwargs())
         rc = self._lib.tsa_align_batch(self.config._h, C.byref(opt), arr, len(pairs), res, err, len(err))
         if rc != 0:
             raise TsaError(rc, err.value.decode(errors="replace"))
@@ -366,7 +384,7 @@ class Aligner:
 
 def align(reference: object, query: object, **kwargs: object) -> Optional[Alignment]:
     """One-call convenience wrapper (mirror of tsalign.align)."""
-    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib", "first_threshold", "traceback", "scout", "dev_flags", "postprocess")}
+    aligner_kwargs = {k: v for k, v in kwargs.items() if k in _ALIGNER_KWARG_NAMES or k in ("alphabet", "device", "lib", "first_threshold", "traceback", "scout", "dev_flags", "postprocess", "flags", "descendant_strategy", "force_label_correcting", "max_template_switches")}
     align_kwargs = {k: v for k, v in kwargs.items() if k not in aligner_kwargs}
     return Aligner(**aligner_kwargs).align(reference, query, **align_kwargs)
 
@@ -382,7 +400,7 @@ class StagedBatch:
         status = C.c_int(0)
         err = C.create_string_buffer(512)
         opt = _options(aligner.no_ts, aligner.device, cost_limit, memory_limit, first_threshold=aligner.first_threshold, traceback=aligner.traceback, scout=aligner.scout,
-                       dev_flags=aligner.dev_flags, postprocess=aligner.postprocess or 0)
+                       dev_flags=aligner.dev_flags, postprocess=aligner.postprocess or 0, **aligner._strategy_kwargs())
         self._h = self._lib.tsa_batch_create(aligner.config._h, C.byref(opt), arr, self.n, C.byref(status), err, len(err))
         if not self._h:
             raise TsaError(status.value, err.value.decode(errors="replace"))

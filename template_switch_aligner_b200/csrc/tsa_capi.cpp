@@ -22,7 +22,7 @@ using namespace tsa;
 // A parsed cost model plus the engines (device buffers, stream) that tsa_align_batch reuses from call to call.
 struct tsa_config {
     HostConfig host;
-    std::mutex lock;
+    std::mutex lock[16];                   // one call at a time per (config, device); calls on different devices run concurrently
     std::unique_ptr<Engine> engine[16];
     std::unique_ptr<Engine> engine2[16];   // second engine (own stream and buffers) for the other half of a large batch
 };
@@ -87,7 +87,7 @@ void encode_pairs(const HostConfig& cfg, const tsa_pair* pairs, size_t n, Encode
 // Unit ops -> the run-length encoded list the reference emits (a_star_aligner.rs:100-122, alignment_type.rs:101-139).
 // Entrance / exit multiplicities are the artefacts of the reference's +-1 walks: |first_offset| + 1
 // (reverse) or |first_offset| (forward) for an entrance, |length_difference| + 1 for an exit.
-void assemble_ops(tsa_result& r, const PairCost& pc) {
+void assemble_ops(tsa_result& r, const PairCost& pc, bool keep_flank_runs) {
     std::vector<tsa_op> out;
     size_t rec = 0;
     for (uint8_t u : pc.ops) {
@@ -113,7 +113,7 @@ void assemble_ops(tsa_result& r, const PairCost& pc) {
         // merged run carries the label of its last operation (a_star_aligner.rs:100-122 walks the path backwards)
         if (!out.empty()) {
             const int32_t pt = out.back().type;
-            const bool same = pt == (int32_t)u || (pt < 8 && u < 8 && (pt & 3) == (u & 3));
+            const bool same = pt == (int32_t)u || (!keep_flank_runs && pt < 8 && u < 8 && (pt & 3) == (u & 3));
             if (same) { out.back().count++; out.back().type = u; continue; }
         }
         tsa_op op;
@@ -137,14 +137,14 @@ void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
             r.result_type = TSA_EXCEEDED_COST_LIMIT; r.cost = opt.cost_limit;
         } else {
             r.result_type = TSA_FOUND_TARGET; r.cost = (uint64_t)pc.cost; r.template_switches = pc.layers;
-            if (pc.trace_status == TRACE_OK) assemble_ops(r, pc);
+            if (pc.trace_status == TRACE_OK) assemble_ops(r, pc, (opt.flags & TSA_FLAG_KEEP_FLANK_RUNS) != 0);
             else if (pc.trace_status != TRACE_SKIPPED) { r.status = TSA_ERR_INTERNAL; snprintf(r.message, sizeof(r.message), "traceback failed (code %d)", pc.trace_status); }
         }
         break;
     case PAIR_NO_TARGET: r.status = TSA_OK; r.result_type = TSA_NO_TARGET; break;
     case PAIR_ERR_TOO_LONG: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "template-switch column windows exceed 1056 columns at this cost threshold"); break;
     case PAIR_ERR_COST_RANGE: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "alignment cost exceeds the kernels' integer range (2^14 with template switches, else 2^26)"); break;
-    case PAIR_ERR_LAYER_CAP: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "more template switches than max_template_switches still improve the cost"); break;
+    case PAIR_ERR_LAYER_CAP: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "not proven optimal within max_template_switches template switches: refused"); break;
     case PAIR_ERR_FLANKS: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "flank lengths above 255 are not supported"); break;
     default: r.status = TSA_ERR_ARGUMENT; break;
     }
@@ -361,8 +361,12 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     const tsa_options o = opt ? *opt : default_options();
     auto t0 = std::chrono::steady_clock::now();
     tsa_config* mcfg = const_cast<tsa_config*>(cfg);
-    std::lock_guard<std::mutex> guard(mcfg->lock);   // one call at a time per config object (context-per-config)
-    const int slot = (o.device >= 0 && o.device < 16) ? o.device : 0;
+    if (o.device < 0 || o.device >= 16 || o.device >= std::max(1, tsa_device_count())) {
+        set_err(err, errcap, tsa_device_count() ? "invalid CUDA device index" : "no CUDA device available: tsalign_b200 has no CPU path");
+        return TSA_ERR_NO_DEVICE;
+    }
+    const int slot = o.device;
+    std::lock_guard<std::mutex> guard(mcfg->lock[slot]);   // one call at a time per (config, device)
     if (!mcfg->engine[slot] || !mcfg->engine[slot]->ok()) mcfg->engine[slot].reset(new Engine(cfg->host, o.device));
     Engine& engine = *mcfg->engine[slot];
     if (!engine.ok()) {
@@ -423,7 +427,11 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     return TSA_OK;
 } catch (const std::exception& e) {
     // e.g. cudaMalloc failure: drop the cached engine (its buffers) and report; nothing is thrown across the ABI
-    if (cfg) { tsa_config* mcfg = const_cast<tsa_config*>(cfg); std::lock_guard<std::mutex> guard(mcfg->lock); for (auto& en : mcfg->engine) en.reset(); for (auto& en : mcfg->engine2) en.reset(); }
+    if (cfg && opt && opt->device >= 0 && opt->device < 16) {
+        tsa_config* mcfg = const_cast<tsa_config*>(cfg);
+        std::lock_guard<std::mutex> guard(mcfg->lock[opt->device]);
+        mcfg->engine[opt->device].reset(); mcfg->engine2[opt->device].reset();
+    }
     set_err(err, errcap, e.what());
     return TSA_ERR_INTERNAL;
 }

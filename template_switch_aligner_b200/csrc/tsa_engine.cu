@@ -41,6 +41,20 @@ struct HostBuf {
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 
+#ifndef TSA_EMUL
+// Function attributes (dynamic shared memory opt-in) are per device: one flag per (kernel instantiation, device).
+struct PerDeviceOnce {
+    std::atomic<bool> done[64];
+    PerDeviceOnce() { for (auto& d : done) d = false; }
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) return true;
+        return !done[dev].exchange(true);
+    }
+};
+#endif
+
 size_t jump_smem_per_warp(int A, int C) {
     const int LW = 32 * C;
     int KL = 0;
@@ -63,11 +77,10 @@ void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len
     const int warps = jump_warps(A, C);
     const size_t smem = jump_smem_per_warp(A, C) * warps;
 #ifndef TSA_EMUL
-    static std::atomic<bool> attr_set(false);
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         rt::check(cudaFuncSetAttribute(k_ts_jump<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
         rt::check(cudaFuncSetAttribute(k_ts_jump<C, WIN>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
-        attr_set = true;
         if (getenv("TSA_B200_DEBUG")) {
             int blocks = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_ts_jump<C, WIN>, 32 * warps, smem);
@@ -109,7 +122,7 @@ struct Engine::Impl {
     size_t cells = 0, ops_total = 0;
     int max_m = 0, max_n = 0;            // longest query / reference of the staged chunk
     int max_recs = 0;
-    DevBuf cfg, lc, meta, seq, D, DT, seedA, seedB, minvec, scratch, best, best_layer, active, next_active, counters, lists, thr, ub, t0, resolved;
+    DevBuf cfg, lc, meta, seq, D, DT, seedA, seedB, minvec, scratch, best, best_layer, active, next_active, counters, lists, thr, ub, t0, resolved, capped;
     std::vector<PairMeta> metas;
     std::vector<uint8_t> seqpool;
     std::vector<int> status;            // per staged pair (PairStatus)
@@ -122,7 +135,7 @@ struct Engine::Impl {
     AlignOptions opt;
     Chunk ck = Chunk();
     bool ts_enabled = false;
-    std::vector<int> h_best, h_layer, h_active;
+    std::vector<int> h_best, h_layer, h_active, h_capped;
     HostBuf h_ops, h_recs, h_small;      // pinned staging of the traceback output
 #ifndef TSA_EMUL
     cudaEvent_t ev[4];
@@ -255,7 +268,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.scratch_bytes = scr * 4;
     I.best.ensure(n * 4); I.best_layer.ensure(n * 4); I.active.ensure(n * 4); I.next_active.ensure(n * 4);
     I.counters.ensure(64);
-    I.thr.ensure(n * 4); I.ub.ensure(n * 4); I.t0.ensure(n * 4); I.resolved.ensure(n * 4);
+    I.thr.ensure(n * 4); I.ub.ensure(n * 4); I.t0.ensure(n * 4); I.resolved.ensure(n * 4); I.capped.ensure(n * 4);
     if (I.ts_enabled) { I.D.ensure(cells * 2); I.DT.ensure(cells * 2); I.seedA.ensure(cells * 4); I.seedB.ensure(cells * 4); }
     if (I.any_win) { I.band.ensure(vec * 8); I.winflag.ensure(n * 4); }
     if (I.flank) { I.PA.ensure(cells * 6); I.PB.ensure(cells * 6); I.tgt_key.ensure(n * 4); I.best_plane.ensure(n * 4); }
@@ -295,7 +308,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.active = I.active.as<int>();
     ck.next_active = I.next_active.as<int>();
     ck.counters = I.counters.as<int>();
-    ck.thr = I.thr.as<int>(); ck.ub = I.ub.as<int>(); ck.t0 = I.t0.as<int>(); ck.resolved = I.resolved.as<int>();
+    ck.thr = I.thr.as<int>(); ck.ub = I.ub.as<int>(); ck.t0 = I.t0.as<int>(); ck.resolved = I.resolved.as<int>(); ck.capped = I.capped.as<int>();
     ck.round = 0;
     ck.kind_mask = ~0u;
     ck.pl_in = nullptr; ck.pl_out = nullptr; ck.dir2 = nullptr;
@@ -323,6 +336,7 @@ void Engine::run_staged() {
     const size_t k1_smem = (size_t)K1_WARPS * K1_SMEM_INTS * sizeof(int);
     rt::dev_memset(I.active.p, 0, I.npairs * 4, I.stream);
     rt::dev_memset(I.next_active.p, 0, I.npairs * 4, I.stream);
+    rt::dev_memset(I.capped.p, 0, I.npairs * 4, I.stream);
     if (!I.ts_enabled) { run_wave(); run_trace(); return; }
     if (I.any_win) rt::dev_memset(I.winflag.p, 0, I.npairs * 4, I.stream);
 #ifndef TSA_EMUL
@@ -367,8 +381,8 @@ void Engine::run_staged() {
         const int tiles_x = (I.max_m + 1 + FLANK_FT - 1) / FLANK_FT, tiles_y = (I.max_n + 1 + FLANK_FT - 1) / FLANK_FT;
         auto run = [&](int16_t*& src, int16_t*& dst, int table, int plane0, int count, int final_at_end, int no_report_plane) {
 #ifndef TSA_EMUL
-            static std::atomic<bool> attr_set(false);
-            if (!attr_set) { rt::check(cudaFuncSetAttribute(k_flank_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLANK_SMEM), "cudaFuncSetAttribute"); attr_set = true; }
+            static PerDeviceOnce once;
+            if (once.first()) rt::check(cudaFuncSetAttribute(k_flank_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLANK_SMEM), "cudaFuncSetAttribute");
 #endif
             for (int done = 0; done < count; done += FLANK_FS) {
                 const int ns = std::min(FLANK_FS, count - done);
@@ -482,9 +496,8 @@ void Engine::run_staged() {
     unsigned full_mask = 0, rev_mask = 0;
     for (int k = 0; k < dev_.n_kinds; k++) { full_mask |= 1u << k; if (dev_.kinds[k].d == 1) rev_mask |= 1u << k; }
     const bool scout = I.opt.scout_round && rev_mask != 0 && rev_mask != full_mask;
-    bool capped = false;
     const unsigned clear_gx = (unsigned)std::min<size_t>(512, std::max<size_t>(8, (I.cells / std::max<size_t>(1, I.npairs)) / 8192));   // blocks per pair
-    for (int round = 0; !capped; round++) {
+    for (int round = 0;; round++) {
         I.ck.round = round;
         I.ck.kind_mask = (scout && round == 0) ? rev_mask : full_mask;
         if (round > 0) {   // layer 0 again for the unresolved pairs
@@ -518,14 +531,20 @@ void Engine::run_staged() {
             for (int c = 0; c < N_CLASS; c++) { cur[c] = out + class_off[c]; cur_n[c] = counts[c]; total += counts[c]; }
             which ^= 1;
             if (total == 0) break;
-            if (layer + 1 >= I.opt.max_layers) { capped = true; break; }   // fetch_staged reports the still-active pairs
+            if (layer + 1 >= I.opt.max_layers) {
+                // layer cap: the still-active pairs are refused and leave the deepening loop; the other pairs of the chunk go on
+                for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) {
+                    TSA_LAUNCH(k_cap, dim3((unsigned)((cur_n[c] + 255) / 256)), dim3(256), 0, I.stream, I.ck, cur[c], cur_n[c]);
+                    stats_.launches++;
+                }
+                break;
+            }
             mark(0);
             for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) fill_layer(cur[c], cur_n[c], layer + 1);
             mark(1);
             fill_pending = true;
         }
         stats_.rounds_run = round + 1;
-        if (capped) break;
         if (scout && round == 0) {   // nothing is proven yet: every pair goes into the first full round, same threshold
             for (int c = 0; c < N_CLASS; c++) { cur[c] = I.d_class_list[c]; cur_n[c] = (int)I.class_list[c].size(); }
             continue;
@@ -603,11 +622,8 @@ static void launch_trace(const Chunk& ck, const TraceLayers& tl, TraceOut to, De
     const int warps = jump_warps(A, C);
     const size_t smem = jump_smem_per_warp(A, C) * warps;
 #ifndef TSA_EMUL
-    static std::atomic<bool> attr_set(false);
-    if (!attr_set) {
-        rt::check(cudaFuncSetAttribute(k_traceback<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
-        attr_set = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) rt::check(cudaFuncSetAttribute(k_traceback<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
 #endif
     const long long stride = (long long)(rows_max + 1) * 3 * 32 * C;   // shorts per warp
     const long long budget = (long long)1 << 29;                        // 1 GiB of shorts-pairs scratch per slice
@@ -670,6 +686,8 @@ void Engine::fetch_staged(PairCost* out) {
     rt::d2h(I.h_best.data(), I.best.p, n * 4, I.stream);
     rt::d2h(I.h_layer.data(), I.best_layer.p, n * 4, I.stream);
     rt::d2h(I.h_active.data(), I.active.p, n * 4, I.stream);
+    I.h_capped.resize(n);
+    rt::d2h(I.h_capped.data(), I.capped.p, n * 4, I.stream);
     std::vector<int> h_sat;
     if (!I.ts_enabled) { h_sat.resize(n); rt::d2h(h_sat.data(), I.next_active.p, n * 4, I.stream); }   // k_affine_wave: boundary values saturated
     I.h_winflag.assign(n, 0);
@@ -683,11 +701,11 @@ void Engine::fetch_staged(PairCost* out) {
         if (pc.status != PAIR_OK) continue;
         if (I.h_winflag[i] & 2) { pc.status = PAIR_ERR_TOO_LONG; continue; }   // a column window did not fit the widest class
         if (!I.ts_enabled && h_sat[i] && I.h_best[i] >= WAVE_SAT) { pc.status = PAIR_ERR_COST_RANGE; continue; }   // exact only below 2^26 - 1
+        if (I.ts_enabled && (I.h_active[i] || I.h_capped[i])) { pc.status = PAIR_ERR_LAYER_CAP; continue; }
         if (I.h_best[i] >= INF32) { pc.status = PAIR_NO_TARGET; continue; }
         // The jump kernel computes in saturating s16: every path cheaper than INF16 is exact, so a result below
         // INF16 is the optimum; above it a cheaper template-switch path may have been saturated away.
         if (I.ts_enabled && I.h_best[i] >= INF16 - 1) { pc.status = PAIR_ERR_COST_RANGE; continue; }
-        if (I.ts_enabled && I.h_active[i]) { pc.status = PAIR_ERR_LAYER_CAP; continue; }
         pc.status = PAIR_OK;
         pc.cost = I.h_best[i];
         pc.layers = I.h_layer[i];

@@ -100,6 +100,7 @@ struct Chunk {
     int* ub;                 // [pair] pruning bound: candidates with cost >= ub are dropped (<= thr, tightened as targets are found)
     int* t0;                 // [pair] target cost of layer 0 (no template switch)
     int* resolved;           // [pair] optimum proven
+    int* capped;             // [pair] still had seeds below the bound after max_layers template switches: refused (PAIR_ERR_LAYER_CAP)
     int round;               // deepening round (0 = first)
     unsigned kind_mask;      // kinds (index into DevConfig::kinds) evaluated by the jump kernel in this round
     // ---- flank planes (left/right flank lengths > 0); all null / 0 otherwise -------------------

@@ -5,6 +5,7 @@ from oracle import oracle
 from helpers import clean_record, config_to_text, parse_config_any
 import randcfg
 import template_switch_aligner_b200 as tsa
+from template_switch_aligner_b200 import api
 
 
 def end_points(ops, ri, qi):
@@ -28,31 +29,54 @@ def end_points(ops, ri, qi):
     return ri, qi
 
 
-def check_alignment(flat, p, g, label=""):
+def merge_flank_runs(ops):
+    """The reference's run-length rule (alignment_type.rs:101-121, a_star_aligner.rs:100-122): flank and non-flank variants of a
+    primary operation repeat each other, a merged run carries the label of its last operation."""
+    out = []
+    for o in ops:
+        if out and o.type < 8 and out[-1].type < 8 and (o.type & 3) == (out[-1].type & 3):
+            out[-1] = oracle.Op(out[-1].count + o.count, o.type)
+        else:
+            out.append(oracle.Op(o.count, o.type, o.primary, o.secondary, o.direction, o.value))
+    return out
+
+
+def check_alignment(flat, p, g, label="", merged=None):
     """The returned alignment must rescore to the returned cost under the reference cost function
     (compute_cost restatement, template_switch_specifics.rs:591-835) and span exactly the requested range.
     With flank lengths > 0 the reference's run-length encoding merges flank and non-flank operations
-    (alignment_type.rs:101-121) and its compute_cost is todo!() there: only the end points are checked (the traceback
-    kernel itself verifies that the edge costs of its path sum to the optimum, else status TSA_ERR_INTERNAL)."""
+    (alignment_type.rs:101-121) and its compute_cost is todo!() there: the alignment is requested with
+    TSA_FLAG_KEEP_FLANK_RUNS (flank runs kept apart) and scored as the search charges flank moves (context.rs:225-353);
+    `merged` (the same alignment requested without the flag) must be the reference's merge of it."""
     r, q = p[0], p[1]
     rng = p[2] if len(p) > 2 and p[2] is not None else (0, len(r), 0, len(q))
     assert g.ops is not None, (label, p)
     ops = [oracle.Op(*o) for o in g.ops]
-    if flat.cfg.left_flank_length == 0 and flat.cfg.right_flank_length == 0:
-        cost, er, eq, ok = oracle.rescore(flat, r, q, ops, rng[0], rng[2], as_searched=True)
-        assert ok and (er, eq) == (rng[1], rng[3]), (label, p, tsa.cigar_of(g.ops), cost, g.cost, er, eq)
-        assert cost == g.cost, (label, p, tsa.cigar_of(g.ops), cost, g.cost)
-    else:
-        # merged runs carry the label of their last operation (a_star_aligner.rs:100-122), so the flank table of a unit
-        # operation cannot be recovered from the run-length encoding: walk the coordinates only
-        assert end_points(ops, rng[0], rng[2]) == (rng[1], rng[3]), (label, p, tsa.cigar_of(g.ops))
+    flanks = flat.cfg.left_flank_length != 0 or flat.cfg.right_flank_length != 0
+    cost, er, eq, ok = oracle.rescore(flat, r, q, ops, rng[0], rng[2], as_searched=True)
+    assert ok and (er, eq) == (rng[1], rng[3]), (label, p, tsa.cigar_of(g.ops), cost, g.cost, er, eq)
+    assert cost == g.cost, (label, p, tsa.cigar_of(g.ops), cost, g.cost)
+    if flanks and merged is not None:
+        mops = [oracle.Op(*o) for o in merged.ops]
+        assert merged.cost == g.cost and end_points(mops, rng[0], rng[2]) == (rng[1], rng[3]), (label, p)
+        want = merge_flank_runs(ops)
+        assert [(o.count, o.type, o.value) for o in mops] == [(o.count, o.type, o.value) for o in want], (label, p, tsa.cigar_of(merged.ops))
     assert sum(1 for o in ops if o.type == oracle.OP_TS_EXIT) == g.template_switches
 
 
 def check_batch(aligner, flat, pairs, no_ts=False, label="", expected=None):
     """pairs: [(r, q) | (r, q, range)].  The product's costs must equal the scalar DP oracle's, bit for bit, and its
     alignments must rescore to them.  expected: optional precomputed oracle costs (None = no target)."""
-    got = aligner.align_batch(pairs)
+    flanks = flat.cfg.left_flank_length != 0 or flat.cfg.right_flank_length != 0
+    merged = None
+    if flanks and aligner.traceback:
+        merged = aligner.align_batch(pairs)          # the reference's run-length encoding (flank runs merged)
+        saved = aligner.flags
+        aligner.flags |= api.FLAG_KEEP_FLANK_RUNS
+        got = aligner.align_batch(pairs)
+        aligner.flags = saved
+    else:
+        got = aligner.align_batch(pairs)
     n_ts = 0
     for idx, (p, g) in enumerate(zip(pairs, got)):
         rng = p[2] if len(p) > 2 else None
@@ -67,7 +91,7 @@ def check_batch(aligner, flat, pairs, no_ts=False, label="", expected=None):
             assert g.cost == want_cost, (label, p, g.cost, want_cost)
             n_ts += g.template_switches > 0
             if aligner.traceback:
-                check_alignment(flat, p, g, label)
+                check_alignment(flat, p, g, label, merged[idx] if merged is not None else None)
     return n_ts
 
 

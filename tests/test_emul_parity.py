@@ -146,3 +146,27 @@ def test_flank_tiles_emulated():
         pairs.append((pairs[0][0], pairs[0][1], (3, length - 2, 5, len(pairs[0][1]))))
         n_ts = parity.check_batch(tsa.Aligner(costs=text, lib=emul()), flat, pairs, label=f"flank tiles {lf}/{rf}")
         assert n_ts >= 1
+
+
+def test_layer_cap_mixed_batch_emulated(configs):
+    # max_template_switches below what some pairs of the batch need: those pairs are refused (status 9), every answered pair
+    # still carries the proven optimum -- the cap of one pair must not end the deepening rounds of its batch siblings
+    from template_switch_aligner_b200 import workloads
+    ocfg = parse_config_any(configs["sample"])
+    flat = oracle.FlatConfig(ocfg)
+    pairs = workloads.read_pairs(5, start=11, length=44) + [("ACGTTGCAAGGCTA" * 3, "ACGTTGCAAGGCTA" * 3), ("ACGTACGTACGTAAGT", "ACGTACGTTCGTAAGT")]
+    want = [oracle.dp_align(flat, r, q).cost for r, q in pairs]
+    seen = set()
+    for mts in (1, 2, 3, 64):
+        for thr in (3, 12):
+            aligner = tsa.Aligner(costs=configs["sample"], lib=emul(), max_template_switches=mts, first_threshold=thr)
+            res = aligner.align_batch(pairs)
+            for g, w in zip(res, want):
+                assert g.status in (0, 9), g.message
+                if g.status == 0:
+                    assert g.found and g.cost == w, (mts, thr, g.cost, w)
+                seen.add((mts, g.status))
+            if mts == 64:
+                assert all(g.status == 0 for g in res)
+            assert res[5].status == 0 and res[5].cost == 0
+    assert (1, 9) in seen and (1, 0) in seen
