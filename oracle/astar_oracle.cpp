@@ -41,7 +41,7 @@ enum { EDGE_ROOT = 100, EDGE_SECONDARY_ROOT = 101, EDGE_PRIMARY_REENTRY = 102 };
 //   SECONDARY:               a,b entrance; p,s,d; c=length d_=primary_index e=secondary_index gap
 //   TS_EXIT:                 a,b entrance; p,s,d; d_=primary_index c=anti_primary_gap
 struct Id {
-    i64 a, b, c, d_, e;
+    int32_t a, b, c, d_, e;   // 32-bit coordinates: 28-byte identifiers keep the node pool small (sequences are far below 2^31)
     uint8_t type, gap, p, s, d;
     bool operator==(const Id& o) const {
         return a == o.a && b == o.b && c == o.c && d_ == o.d_ && e == o.e && type == o.type && gap == o.gap && p == o.p && s == o.s && d == o.d;
@@ -52,7 +52,7 @@ struct IdHash {
     size_t operator()(const Id& i) const {
         u64 h = 0x9E3779B97F4A7C15ull;
         auto mix = [&](u64 v) { h = (h ^ v) * 0xff51afd7ed558ccdull; h ^= h >> 29; };
-        mix((u64)i.a); mix((u64)i.b); mix((u64)i.c); mix((u64)i.d_); mix((u64)i.e);
+        mix((u64)(uint32_t)i.a | ((u64)(uint32_t)i.b << 32)); mix((u64)(uint32_t)i.c | ((u64)(uint32_t)i.d_ << 32)); mix((u64)(uint32_t)i.e);
         mix((u64)i.type | ((u64)i.gap << 8) | ((u64)i.p << 16) | ((u64)i.s << 24) | ((u64)i.d << 32));
         return (size_t)h;
     }
@@ -63,14 +63,18 @@ struct Edge {
     i64 value;
 };
 
+static const uint32_t NO_PRED = UINT32_MAX;
+
+// Nodes live in one pool per search (index = identity of an opened node); the predecessor is the pool index of the node that
+// was expanded.  Backtracking still goes through the closed list by *identifier* (a_star_aligner.rs:100-122 looks the
+// predecessor identifier up in the closed list, which holds the best node seen for it), see tsao_astar_align.
 struct Node {
     Id id;
-    Id pred;
-    bool has_pred;
+    uint32_t pred_idx = NO_PRED;
     Edge edge;
     u64 cost, lb;
-    u64 ts_total_length;  // MaxTemplateSwitchTotalLengthStrategy memory
-    u64 ts_count;         // MaxTemplateSwitchCountStrategy memory
+    uint32_t ts_total_length;  // MaxTemplateSwitchTotalLengthStrategy memory
+    uint32_t ts_count;         // MaxTemplateSwitchCountStrategy memory
     u64 f() const { return cost + lb; }
     u64 anti_diagonal() const { return id.type == PRIMARY ? (u64)(id.a + id.b) : UINT64_MAX; }  // identifier.rs:424-441
 };
@@ -129,13 +133,12 @@ struct Problem {
 static Node make_successor(const Problem& pb, const Node& from, const Id& id, u64 inc, const Edge& edge) {
     Node s;
     s.id = id;
-    s.pred = from.id;
-    s.has_pred = true;
+    s.pred_idx = NO_PRED;   // set by the search loop: the pool index of `from`
     s.edge = edge;
     s.cost = checked_add(from.cost, inc);
     s.lb = from.lb > inc ? from.lb - inc : 0;
     u64 len_inc = (edge.type == TSAO_OP_SECONDARY_MATCH || edge.type == TSAO_OP_SECONDARY_SUBSTITUTION || edge.type == TSAO_OP_SECONDARY_INSERTION) ? 1 : 0;
-    s.ts_total_length = pb.opt.total_length_maximise ? from.ts_total_length + len_inc : 0;  // template_switch_total_length.rs:94-108
+    s.ts_total_length = pb.opt.total_length_maximise ? from.ts_total_length + (uint32_t)len_inc : 0;  // template_switch_total_length.rs:94-108
     s.ts_count = from.ts_count;
     return s;
 }
@@ -336,8 +339,48 @@ static void generate_successors(Problem& pb, const Node& node, std::vector<Node>
 // Heap order: best = min (f, cost), then larger anti-diagonal, then larger secondary score
 // (node_ord.rs:41-69 wrapped by comparator.rs:10-17).
 struct HeapItem {
-    u64 f, cost, ad, score;
+    u64 f, cost;
+    uint32_t ad, score;   // anti-diagonal (UINT32_MAX for non-primary nodes, identifier.rs:424-441), total TS length
     uint32_t idx;
+};
+
+// Closed list (generic_a_star/src/closed_lists.rs:45-88): identifier -> pool index of the node kept for it.  Open addressing
+// over 32-bit pool indices; the identifiers are read from the pool.
+struct Store {
+    std::vector<Node> pool;
+    std::vector<uint32_t> slots;   // pool index + 1, 0 = empty
+    size_t count = 0, mask = 0;
+    Store() { slots.assign(1 << 12, 0); mask = slots.size() - 1; }
+    size_t size() const { return count; }
+    // returns the slot of `id` (occupied) or the empty slot where it belongs
+    uint32_t* locate(const Id& id) {
+        size_t h = IdHash()(id) & mask;
+        for (;;) {
+            uint32_t& sl = slots[h];
+            if (sl == 0 || pool[sl - 1].id == id) return &sl;
+            h = (h + 1) & mask;
+        }
+    }
+    const Node* find(const Id& id) { const uint32_t sl = *locate(id); return sl ? &pool[sl - 1] : nullptr; }
+    void put(uint32_t idx) {
+        uint32_t* sl = locate(pool[idx].id);
+        if (*sl == 0) {
+            count++;
+            *sl = idx + 1;
+            if (count * 10 > slots.size() * 6) grow();
+        } else *sl = idx + 1;
+    }
+    void grow() {
+        std::vector<uint32_t> old;
+        old.swap(slots);
+        slots.assign(old.size() * 2, 0);
+        mask = slots.size() - 1;
+        for (uint32_t v : old) if (v) {
+            size_t h = IdHash()(pool[v - 1].id) & mask;
+            while (slots[h]) h = (h + 1) & mask;
+            slots[h] = v;
+        }
+    }
 };
 struct HeapLess {  // "a is worse than b" for std::priority_queue (top = best)
     bool operator()(const HeapItem& a, const HeapItem& b) const {
@@ -358,13 +401,14 @@ struct SearchResult {
 // generic_a_star/src/lib.rs:316-552.  `is_target` and label mode are parameters so the same loop serves the
 // top-level search and the min-length lookahead (template_switch_min_length.rs:651-684).
 template <class IsTarget>
-static SearchResult search(Problem& pb, const Node& root, bool label_setting, IsTarget is_target,
-                           std::unordered_map<Id, Node, IdHash>& closed) {
-    std::vector<Node> pool;
+static SearchResult search(Problem& pb, const Node& root, bool label_setting, IsTarget is_target, Store& closed) {
+    std::vector<Node>& pool = closed.pool;
     std::priority_queue<HeapItem, std::vector<HeapItem>, HeapLess> open;
     auto push = [&](const Node& nd) {
+        if (pool.size() >= (size_t)NO_PRED - 1) abort();   // 32-bit pool indices
         pool.push_back(nd);
-        open.push(HeapItem{nd.f(), nd.cost, nd.anti_diagonal(), nd.ts_total_length, (uint32_t)(pool.size() - 1)});
+        const u64 ad = nd.anti_diagonal();
+        open.push(HeapItem{nd.f(), nd.cost, ad == UINT64_MAX ? UINT32_MAX : (uint32_t)ad, nd.ts_total_length, (uint32_t)(pool.size() - 1)});
     };
     SearchResult res;
     const u64 cost_limit = pb.opt.cost_limit;
@@ -392,25 +436,26 @@ static SearchResult search(Problem& pb, const Node& root, bool label_setting, Is
             if (have_target) break;
             res.type = TSAO_NO_TARGET; res.cost = 0; return res;
         }
-        const Node node = pool[open.top().idx];
+        const uint32_t node_idx = open.top().idx;
+        const Node node = pool[node_idx];
         open.pop();
         if (node.f() > cost_limit) { res.type = TSAO_EXCEEDED_COST_LIMIT; res.cost = cost_limit; return res; }
         if ((u64)closed.size() + (u64)open.size() > node_count_limit) { res.type = TSAO_EXCEEDED_MEMORY_LIMIT; res.cost = node.cost; return res; }
         if (node.f() > target_cost) break;
 
         const bool tgt = is_target(node);
-        auto it = closed.find(node.id);
+        const Node* it = closed.find(node.id);
         bool skip = false;
-        if (it != closed.end()) skip = label_setting ? true : !node_better(node, it->second);
+        if (it) skip = label_setting ? true : !node_better(node, *it);
         if (skip) {
             res.suboptimal++;
-            const u64 existing_cost = it->second.cost, existing_score = it->second.ts_total_length;
+            const u64 existing_cost = it->cost, existing_score = it->ts_total_length;
             if (tgt && (node.cost < std::min(target_cost, existing_cost) ||
                         (node.cost == std::min(target_cost, existing_cost) && node.ts_total_length > std::max(target_score, existing_score)))) {
                 have_target = true; target_id = node.id; target_cost = node.cost; target_score = node.ts_total_length;
-                if (label_setting) { closed[node.id] = node; res.closed++; break; }
+                if (label_setting) { closed.put(node_idx); res.closed++; break; }
             } else if (tgt && (existing_cost < target_cost || (existing_cost == target_cost && node.ts_total_length > existing_score))) {
-                have_target = true; target_id = it->second.id; target_cost = it->second.cost; target_score = it->second.ts_total_length;
+                have_target = true; target_id = it->id; target_cost = it->cost; target_score = it->ts_total_length;
                 if (label_setting) { res.closed++; break; }
             }
             continue;
@@ -418,22 +463,23 @@ static SearchResult search(Problem& pb, const Node& root, bool label_setting, Is
 
         succ.clear();
         generate_successors(pb, node, succ);
-        for (const Node& s : succ) {
+        for (Node& s : succ) {
+            s.pred_idx = node_idx;
             if (s.f() <= cost_limit) { push(s); res.opened++; }
             else applied_cost_limit = true;
         }
 
         if (tgt && (node.cost < target_cost || (node.cost == target_cost && node.ts_total_length > target_score))) {
             have_target = true; target_id = node.id; target_cost = node.cost; target_score = node.ts_total_length;
-            if (label_setting) { closed[node.id] = node; res.closed++; break; }
+            if (label_setting) { closed.put(node_idx); res.closed++; break; }
         }
-        closed[node.id] = node;
+        closed.put(node_idx);
         res.closed++;
     }
     if (!have_target) { res.type = TSAO_NO_TARGET; res.cost = 0; return res; }
     res.type = TSAO_FOUND_TARGET;
     res.target = target_id;
-    res.cost = closed.find(target_id)->second.cost;
+    res.cost = closed.find(target_id)->cost;
     return res;
 }
 
@@ -446,7 +492,7 @@ static bool lookahead(Problem& pb, Node& root) {
         root.lb = std::max(root.lb, it->second);
         return true;
     }
-    std::unordered_map<Id, Node, IdHash> closed;
+    Store closed;
     const u64 ml = pb.cfg.min_length;
     tsao_options saved = pb.opt;
     pb.opt.min_length_lookahead = 0;  // nested graph never reaches an entrance
@@ -495,9 +541,9 @@ extern "C" int tsao_astar_align(const tsao_config* c, const uint8_t* reference, 
 
     Node root{};  // context.rs:112-123
     root.id.type = PRIMARY; root.id.a = ro; root.id.b = qo; root.id.c = 0; root.id.gap = GAP_NONE;
-    root.has_pred = false; root.edge = Edge{EDGE_ROOT, 0, 0, 0, 0};
+    root.pred_idx = NO_PRED; root.edge = Edge{EDGE_ROOT, 0, 0, 0, 0};
 
-    std::unordered_map<Id, Node, IdHash> closed;
+    Store closed;
     SearchResult r = search(pb, root, pb.label_setting(),
                             [&](const Node& nd) { return (nd.id.type == PRIMARY || nd.id.type == PRIMARY_REENTRY) && nd.id.a == rl && nd.id.b == ql; },  // context.rs:731-748
                             closed);
@@ -509,15 +555,15 @@ extern "C" int tsao_astar_align(const tsao_config* c, const uint8_t* reference, 
 
     // a_star_aligner.rs:100-122: walk predecessor edges target -> root, drop internal ops, merge runs.
     std::vector<std::pair<i64, Edge>> rle;
-    const Node* cur = &closed.find(r.target)->second;
+    const Node* cur = closed.find(r.target);
     out->ts_total_length = cur->ts_total_length;
-    while (cur->has_pred) {
+    while (cur->pred_idx != NO_PRED) {
         const Edge& e = cur->edge;
         if (e.type < 100) {
             if (!rle.empty() && is_repeated(e, rle.back().second)) rle.back().first++;
             else rle.push_back({1, e});
         }
-        cur = &closed.find(cur->pred)->second;
+        cur = closed.find(closed.pool[cur->pred_idx].id);   // the closed list's node for the predecessor identifier
     }
     std::reverse(rle.begin(), rle.end());
     out->n_ops = (i64)rle.size();

@@ -57,12 +57,14 @@ TSA_DEV uint32_t addmin_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __via
 TSA_DEV uint32_t min3_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 TSA_DEV uint32_t min_s16x2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 TSA_DEV uint32_t add_s16x2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+TSA_DEV uint32_t cmplt_s16x2(uint32_t a, uint32_t b) { return __vcmplts2(a, b); }                 // per half: 0xffff where a < b (signed)
 TSA_DEV int atomic_min_s32(int* p, int v) { return atomicMin(p, v); }
 TSA_DEV int atomic_or_s32(int* p, int v) { return atomicOr(p, v); }
 TSA_DEV int atomic_max_s32(int* p, int v) { return atomicMax(p, v); }
 TSA_DEV int atomic_and_s32(int* p, int v) { return atomicAnd(p, v); }
 TSA_DEV int atomic_add_s32(int* p, int v) { return atomicAdd(p, v); }
 TSA_DEV int clz_u32(uint32_t v) { return __clz((int)v); }
+TSA_DEV int ffs_u32(uint32_t v) { return __ffs((int)v); }                                          // 1-based index of the lowest set bit, 0 if none
 // producer / consumer flags between warps of one launch (k_affine_wave): release store, acquire load, L2 data load
 TSA_DEV int ld_acquire_s32(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 TSA_DEV void st_release_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -159,12 +161,14 @@ inline uint32_t min3_s16x2(uint32_t a, uint32_t b, uint32_t c) {
 }
 inline uint32_t min_s16x2(uint32_t a, uint32_t b) { return pack16(std::min<int>(lo16(a), lo16(b)), std::min<int>(hi16(a), hi16(b))); }
 inline uint32_t add_s16x2(uint32_t a, uint32_t b) { return pack16((int16_t)(lo16(a) + lo16(b)), (int16_t)(hi16(a) + hi16(b))); }
+inline uint32_t cmplt_s16x2(uint32_t a, uint32_t b) { return (lo16(a) < lo16(b) ? 0xffffu : 0u) | (hi16(a) < hi16(b) ? 0xffff0000u : 0u); }
 inline int atomic_min_s32(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
 inline int atomic_or_s32(int* p, int v) { int o = *p; *p = o | v; return o; }
 inline int atomic_max_s32(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 inline int atomic_and_s32(int* p, int v) { int o = *p; *p = o & v; return o; }
 inline int atomic_add_s32(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline int clz_u32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+inline int ffs_u32(uint32_t v) { return __builtin_ffs((int)v); }
 inline int ld_acquire_s32(const int* p) { return *(const volatile int*)p; }
 inline void st_release_s32(int* p, int v) { *(volatile int*)p = v; }
 inline int ld_cg_s32(const int* p) { return *(const volatile int*)p; }

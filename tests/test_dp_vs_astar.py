@@ -93,3 +93,22 @@ def test_cost_limit(configs):
     # by the limit, even though a target within the limit exists.  The DP reports FoundTarget.
     assert oracle.astar_align(flat, r, q, cost_limit=2).result_type == "ExceededCostLimit"
     assert oracle.dp_align(flat, r, q, cost_limit=2).found
+
+
+def test_c2_pairs_against_completed_astar():
+    """BASELINE config 2 at its named size: the restated reference A* was run to completion offline on seeded 150 bp read pairs
+    (tests/golden/make_astar_c2.py; the hard ones open 10^8 nodes) -- the layered DP must return the same optimal costs."""
+    from conftest import load_golden
+    from template_switch_aligner_b200 import workloads
+    golden = load_golden("astar_c2.json")
+    flat = oracle.FlatConfig(tsa_config.parse(workloads.sample_config_text(), "dna-n"))
+    checked = 0
+    for rec in golden["pairs"]:
+        if rec["result"] != "FoundTarget":
+            continue
+        r, q = workloads.read_pair(rec["index"], 150)
+        assert (len(r), len(q)) == (rec["reference_len"], rec["query_len"])
+        d = oracle.dp_align(flat, r, q)
+        assert d.found and d.cost == rec["cost"], (rec["index"], d.cost, rec["cost"])
+        checked += 1
+    assert checked >= 32 and max(rec.get("opened_nodes", 0) for rec in golden["pairs"]) > 5e7   # hard pairs included

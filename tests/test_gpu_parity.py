@@ -143,6 +143,40 @@ def test_read_pair_batch_gpu(lib):
     assert n_ts >= 48  # the planted TSMs are found
 
 
+def test_c2_pairs_against_completed_astar_gpu(lib):
+    # GPU == the reference's own algorithm at config 2 size: costs of the restated A* run to completion offline
+    # (tests/golden/astar_c2.json, make_astar_c2.py; hard pairs open 10^8 nodes), alignments rescored
+    from conftest import load_golden
+    golden = load_golden("astar_c2.json")
+    text = workloads.sample_config_text()
+    flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+    recs = [rec for rec in golden["pairs"] if rec["result"] == "FoundTarget"]
+    pairs = [workloads.read_pair(rec["index"], 150) for rec in recs]
+    assert len(pairs) >= 32
+    got = tsa.Aligner(costs=text, lib=lib).align_batch(pairs)
+    for rec, p, g in zip(recs, pairs, got):
+        assert g.status == 0 and g.found and g.cost == rec["cost"], (rec["index"], g.cost, rec["cost"])
+        parity.check_alignment(flat, p, g, "astar c2")
+
+
+def test_c3_shape_against_oracle_gpu(lib):
+    # BASELINE config 3 at its named shape: 1 kb pairs with 5 planted switches (and 190-500 bp pairs that straddle several
+    # 64 x 64 tiles of k_flank_fused) under flank lengths 50 / 50 -- 101 planes per layer.  Costs of the scalar DP oracle
+    # computed offline (tests/golden/c3_costs.json, make_c3_costs.py); flank alignments rescored (TSA_FLAG_KEEP_FLANK_RUNS)
+    from conftest import load_golden
+    golden = load_golden("c3_costs.json")
+    text = workloads.sample_config_text().replace("left_flank_length = 0", "left_flank_length = 50").replace("right_flank_length = 0", "right_flank_length = 50")
+    flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+    cases, want = [], []
+    for key, cost in sorted(golden.items()):
+        length, index, n_tsm = map(int, key.split("|"))
+        cases.append(workloads.long_pair(index, length, n_tsm=n_tsm)); want.append(cost)
+    assert sum(len(c[0]) == 1000 for c in cases) >= 8 and len(cases) >= 12
+    aligner = tsa.Aligner(costs=text, lib=lib)
+    n_ts = parity.check_batch(aligner, flat, cases, label="c3", expected=want)
+    assert n_ts >= 8
+
+
 def test_full_size_properties_gpu(lib):
     # BASELINE config 2 at batch scale (no oracle): size-independent properties of the optimum
     text = workloads.sample_config_text()
