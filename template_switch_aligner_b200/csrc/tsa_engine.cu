@@ -6,6 +6,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <stdexcept>
 
 #include "tsa_kernels.cuh"
 
@@ -64,6 +65,16 @@ size_t jump_smem_per_warp(int A, int C) {
     return sub_bytes + (size_t)KL * LW * 4 + JUMP_GAP_BYTES;
 }
 
+// Row kernel (k_ts_jump<C, false, true>): substitution table + gap costs only; evaluation kernel (k_ts_eval): range-minimum levels.
+size_t row_smem_per_warp(int A, int C) { return (((size_t)A * 32 * C * 2 + 15) & ~(size_t)15) + JUMP_GAP_BYTES; }
+size_t eval_smem_per_warp(int C) {
+    const int LW = 32 * C;
+    int KL = 0;
+    while ((1 << (KL + 1)) <= LW) KL++;
+    return (size_t)(KL + 1) * LW * 4;
+}
+constexpr int MAX_Q_SLICES = 2048;
+
 int jump_warps(int A, int C) {
     const size_t per = jump_smem_per_warp(A, C);
     int w = K2_WARPS;
@@ -102,6 +113,61 @@ void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len
     }
 }
 
+// Pairs without column windows: row kernel -> row queue -> evaluation kernel, in slices of pairs whose candidate rows fit the queue.
+// counts[slice] receives the slots each slice asked for (the caller compares them with the capacity after the layer).
+template <int C>
+void launch_jump_split(Chunk ck, int stage, const int* d_list, int n_list, int max_len, int A, int n_kinds, int ml, cudaStream_t stream, long long& launches,
+                       int slice_pairs, int* d_counts, int& n_slices, std::vector<int>& slice_size) {
+    ck.win_stage = stage;
+    const int warps = jump_warps(A, C);
+    const size_t smem_row = row_smem_per_warp(A, C) * warps, smem_eval = eval_smem_per_warp(C) * warps;
+    int eval_blocks = 2;
+#ifndef TSA_EMUL
+    static PerDeviceOnce once;
+    static std::atomic<int> resident[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (once.first()) {
+        auto row = k_ts_jump<C, false, true>;
+        auto eval = k_ts_eval<C>;
+        rt::check(cudaFuncSetAttribute(row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
+        rt::check(cudaFuncSetAttribute(row, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
+        rt::check(cudaFuncSetAttribute(eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
+        rt::check(cudaFuncSetAttribute(eval, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
+        cudaDeviceProp prop;
+        rt::check(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+        int per_sm = 0;
+        rt::check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eval, 32 * warps, smem_eval), "occupancy");
+        resident[dev & 63] = std::max(1, per_sm) * prop.multiProcessorCount;
+        if (getenv("TSA_B200_DEBUG")) {
+            cudaFuncAttributes fa, fb;
+            cudaFuncGetAttributes(&fa, row); cudaFuncGetAttributes(&fb, eval);
+            int row_blocks = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_blocks, row, 32 * warps, smem_row);
+            fprintf(stderr, "[tsalign_b200] C=%d: row kernel %d regs, %d blocks/SM; eval kernel %d regs, %d blocks/SM\n", C, fa.numRegs, row_blocks, fb.numRegs, per_sm);
+        }
+    }
+    eval_blocks = resident[dev & 63];
+#endif
+    const int n_ep = (max_len - ml + 2) / 2;
+    if (n_ep <= 0 || n_kinds <= 0) return;
+    const int tasks = n_kinds * n_ep;
+    const unsigned gx = (unsigned)((tasks + warps - 1) / warps);
+    slice_pairs = std::max(1, std::min(slice_pairs, 65535));
+    for (int off = 0; off < n_list; off += slice_pairs) {
+        const int cnt = std::min(slice_pairs, n_list - off);
+        if (n_slices >= MAX_Q_SLICES) throw std::runtime_error("row queue: too many slices in one layer");
+        ck.q_count = d_counts + n_slices;
+        slice_size.push_back(cnt);
+        n_slices++;
+        auto row = k_ts_jump<C, false, true>;
+        auto eval = k_ts_eval<C>;
+        TSA_LAUNCH(row, dim3(gx, (unsigned)cnt), dim3(32 * warps), smem_row, stream, ck, d_list + off, cnt);
+        TSA_LAUNCH(eval, dim3((unsigned)eval_blocks), dim3(32 * warps), smem_eval, stream, ck);
+        launches += 2;
+    }
+}
+
 }  // namespace
 
 struct Engine::Impl {
@@ -113,6 +179,9 @@ struct Engine::Impl {
     bool flank = false;
     DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b, tables;
     DevBuf band, winflag;                             // column windows: band vectors of the fill, overflow flags
+    DevBuf q_hdr, q_rows, q_counts;                   // row queue between the row kernel and the evaluation kernel
+    size_t q_cap = 0;                                 // slots
+    double q_est[N_CLASS] = {0};                      // learned demand of queue slots per pair, by class (sizes the slices)
     bool any_win = false;
     std::vector<int> h_winflag;
     DevBuf wave_prefix, wave_ticket;   // k_affine_wave: first ticket per pair, ticket counter
@@ -463,18 +532,58 @@ void Engine::run_staged() {
         stats_.chains_run += h[1]; stats_.rows_filled += h[2]; stats_.rows_jumped += h[3]; stats_.chains_started += h[4];
         for (int c = 0; c < N_CLASS; c++) counts8[c] = h[8 + c];
     };
+    // Row queue of the split jump (classes without column windows): sized from the learned demand per pair, at least the worst case
+    // of one pair (every row of every chain queued), at most 6 GiB.
+    int n_slices = 0;
+    std::vector<int> slice_size, slice_class, h_qcounts;
+    {
+        size_t want = 0, one = 0;
+        int min_lw = 1 << 30;
+        for (int c = 0; c < N_CLASS - 1; c++) {
+            if (I.class_list[c].empty()) continue;
+            const int LW = 32 * CLASS_C[c], mx = I.class_maxlen[c];
+            const int n_ep = std::max(0, (mx - dev_.ml + 2) / 2);
+            const double chains = (double)dev_.n_kinds * n_ep;
+            const double rows_max = (double)std::min(dev_.lmax, mx) + 1 + QUEUE_RESERVE;
+            if (I.q_est[c] <= 0) I.q_est[c] = chains * 2.0;
+            one = std::max(one, (size_t)(chains * rows_max) * LW * 4);
+            want += (size_t)((double)I.class_list[c].size() * I.q_est[c] * 1.3) * LW * 4;
+            min_lw = std::min(min_lw, LW);
+        }
+        if (min_lw < (1 << 30)) {
+            const size_t bytes = std::max(one, std::min(want, (size_t)6 << 30)) + 4096;
+            I.q_rows.ensure(bytes);
+            I.q_hdr.ensure((I.q_rows.cap / ((size_t)min_lw * 4) + 1) * sizeof(QueueHdr));
+            I.q_counts.ensure((size_t)MAX_Q_SLICES * 4);
+        }
+    }
+    auto jump_split = [&](int c, int stage, long long& l) {
+        Chunk ck = I.ck;
+        const int LW = 32 * CLASS_C[c];
+        ck.q_cap = (int)std::min<size_t>(I.q_rows.cap / ((size_t)LW * 4), (size_t)1 << 30);
+        ck.q_hdr = I.q_hdr.as<QueueHdr>();
+        ck.q_rows = I.q_rows.as<uint32_t>();
+        const int slice_pairs = (int)std::max(1.0, std::min(65535.0, (double)ck.q_cap / (I.q_est[c] * 1.3)));
+        const int ml_ = dev_.ml, A_ = dev_.A, nk = dev_.n_kinds, mx = I.class_maxlen[c];
+        int* counts = I.q_counts.as<int>();
+        switch (c) {
+        case 0: launch_jump_split<3>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+        case 1: launch_jump_split<5>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+        case 2: launch_jump_split<9>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+        case 3: launch_jump_split<17>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+        default: launch_jump_split<33>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+        }
+        slice_class.resize(slice_size.size(), c);
+    };
     auto jump_class = [&](int c) {
         long long l = 0;
         const int ml_ = dev_.ml, A_ = dev_.A, nk = dev_.n_kinds, mx = I.class_maxlen[c];
         switch (c) {
-        case 0: launch_jump<3, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break;
-        case 1: launch_jump<5, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break;
-        case 2: launch_jump<9, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break;
-        case 3: launch_jump<17, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break;
+        case 0: case 1: case 2: case 3: jump_split(c, 0, l); break;
         case 4:   // medium: windows of 544 columns, then the whole sequences for the pairs that were flagged
-            if (I.opt.no_windows) { launch_jump<33, false>(I.ck, 0, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l); break; }
+            if (I.opt.no_windows) { jump_split(c, 0, l); break; }
             launch_jump<17, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
-            launch_jump<33, false>(I.ck, 2, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            jump_split(c, 2, l);
             break;
         default:  // long: windows of 544, then of 1056 columns
 #ifdef TSA_EMUL
@@ -489,6 +598,32 @@ void Engine::run_staged() {
             break;
         }
         stats_.launches += l; stats_.jump_launches += l;
+    };
+    // The jump of one layer.  A slice of pairs that asked for more queue slots than there are dropped rows: the learned demand is
+    // updated from the exact count and the jump of the layer is repeated with smaller slices (seeds are minima: repeating is exact).
+    auto jump_layer = [&]() {
+        for (int attempt = 0;; attempt++) {
+            n_slices = 0; slice_size.clear(); slice_class.clear();
+            if (I.q_counts.p) rt::dev_memset(I.q_counts.p, 0, (size_t)MAX_Q_SLICES * 4, I.stream);
+            mark(2);
+            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) jump_class(c);
+            mark(3);
+            if (n_slices == 0) return;
+            h_qcounts.resize((size_t)n_slices);
+            rt::d2h(h_qcounts.data(), I.q_counts.p, (size_t)n_slices * 4, I.stream);
+            rt::stream_sync(I.stream);
+            bool overflow = false;
+            for (int s2 = 0; s2 < n_slices; s2++) {
+                const int c = slice_class[(size_t)s2];
+                const size_t cap = std::min<size_t>(I.q_rows.cap / ((size_t)32 * CLASS_C[c] * 4), (size_t)1 << 30);
+                I.q_est[c] = std::max(I.q_est[c], (double)h_qcounts[(size_t)s2] / std::max(1, slice_size[(size_t)s2]));
+                if ((size_t)h_qcounts[(size_t)s2] > cap) {
+                    overflow = true;
+                    if (slice_size[(size_t)s2] == 1 || attempt > 8) throw std::runtime_error("row queue: one pair does not fit the queue");
+                }
+            }
+            if (!overflow) return;
+        }
     };
     // Scouting round: the reverse kinds (anti-diagonal geometry, no trivial self matches) are cheap to evaluate and
     // usually already contain the optimum.  Running them alone first gives the full rounds a tight upper bound, so
@@ -514,9 +649,7 @@ void Engine::run_staged() {
                     TSA_LAUNCH(k_clear_seeds, dim3(clear_gx, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, cur[c] + off, cnt);
                     stats_.launches++;
                 }
-            mark(2);
-            for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) jump_class(c);
-            mark(3);
+            jump_layer();
             int* out = spare[which];
             for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) {
                 TSA_LAUNCH(k_advance, dim3((unsigned)((cur_n[c] + 255) / 256)), dim3(256), 0, I.stream, I.ck, cur[c], cur_n[c], out + class_off[c], 8 + c);

@@ -78,6 +78,18 @@ constexpr int DIR2_I_SEED = 2;    //                       I state taken from th
 constexpr int KEY_PLANES = 512;   // tgt_key = cost * KEY_PLANES + plane index
 constexpr int KEY_INF = 0x7f7f7f7f;   // memset-able
 
+// One candidate row of a chain pair, handed from the row kernel (k_ts_jump<C, false, true>) to the evaluation kernel (k_ts_eval):
+// the start costs of the row's columns follow in Chunk::q_rows (32 * C packed words per slot).
+struct QueueHdr {
+    int kk;                  // kind index | flags << 8 (bit 0 / 1: the low / high chain can still produce a seed below the bound); < 0: reserved slot that was not used
+    int b;                   // pair
+    int e0, ip;              // primary end of the low chain (the high chain ends at e0 + 1), entrance row
+    int lc0, lc1;            // length costs of the two chains at this row (INF32: no exit)
+    int rmD;                 // row minimum of D at the entrance row, clamped to 2^20
+    int T;                   // pruning bound of the pair during this launch
+};
+constexpr int QUEUE_RESERVE = 4;   // slots a warp reserves per atomic
+
 // Everything a kernel needs about the resident chunk of pairs.
 struct Chunk {
     const PairMeta* pairs;
@@ -117,6 +129,11 @@ struct Chunk {
     int* winflag;            // [pair] bit 0: a chain's window did not fit the first-stage class in this layer (redo in the second
                              // stage); bit 1: it did not fit the widest class either (the pair is refused)
     int win_stage;           // 0: not a windowed launch; 1: first stage; 2: second stage (only pairs with bit 0 set)
+    // ---- row queue between the row kernel and the evaluation kernel (pairs that run without column windows) ---------------
+    int* q_count;            // slots reserved in this launch (may exceed q_cap: the host then repeats the layer with smaller slices)
+    int q_cap;               // slots of q_hdr / q_rows
+    QueueHdr* q_hdr;
+    uint32_t* q_rows;        // [slot][32 * C]: start costs of the row (both chains packed), "infinite" where no start is allowed
     int* counters;           // [0] pairs with next_active, [1..4] work statistics, [8 + class] compacted list sizes
 };
 
