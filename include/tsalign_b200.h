@@ -146,6 +146,45 @@ void tsa_batch_timing(const tsa_batch* batch, double* jump_ms, double* fill_ms);
 void tsa_batch_work(const tsa_batch* batch, int64_t* chains_started, int64_t* chains_run, int64_t* rows_filled, int64_t* rows_jumped);
 void tsa_batch_free(tsa_batch* batch);
 
+/* ---- one very long pair without template switches, column-banded over several GPUs (BASELINE config 5) ----------------------
+ * What `tsalign align --no-ts --memory-limit B` (tsalign/src/align.rs:57-223) is asked for on a pair whose search does not fit the
+ * limit: the reference's A* gives up with AStarResult::ExceededMemoryLimit (generic_a_star/src/lib.rs:332-335,380-389).  Here the
+ * limit (tsa_options.memory_limit, bytes per device) bounds what is resident -- checkpoint rows, boundary columns and the codes of
+ * one tile instead of a code matrix -- and the alignment is still produced; TSA_EXCEEDED_MEMORY_LIMIT is returned only when not even
+ * the coarsest checkpoint spacing fits.  The query columns are cut into bands, one per device; the last column of a band streams
+ * into the next device's memory with plain 8-byte stores over NVLink (peer access), no collective. */
+typedef struct {
+    double forward_ms, trace_ms;       /* device time of the band's forward launch; host wall time of its share of the traceback */
+    int64_t tiles, tile_cells;         /* tiles recomputed with codes by the traceback, and their cells */
+    int64_t boundary_bytes_out;        /* bytes this band stored into the next device's memory (8 per row) */
+    int64_t resident_bytes;            /* device memory the band held */
+    int32_t interval, group;           /* rows between checkpoint rows / 256-column strips between kept boundary columns */
+} tsa_long_stats;
+/* All bands driven by this process (one host thread; devices[k] = CUDA device of band k, neighbours need peer access).
+ * interval / group: 0 = chosen by the library.  stats: n_devices entries or NULL.  opt->no_ts must be set. */
+int tsa_align_long(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pair, const int32_t* devices, int32_t n_devices,
+                   int32_t interval, int32_t group, tsa_result* out, tsa_long_stats* stats, char* err, size_t errcap);
+
+/* The same, one band per process (torchrun: rank r drives device opt->device).  Protocol: every rank creates its band, exports the
+ * handle of its incoming boundary buffer, connects to the handle of rank + 1 (ranks exchange the 64 bytes however they like),
+ * a barrier, then every rank calls tsa_long_forward concurrently.  The traceback starts on the last rank with
+ * {nn, mm, 0, 1, cost, 0} and is passed to tsa_long_owner(column) whenever a walk returns with status 0. */
+typedef struct tsa_long tsa_long;
+typedef struct { int32_t i, j, g, need; int64_t cost; int32_t status, reserved; } tsa_long_walk_state;   /* status: 0 handed to the left, 1 root reached, < 0 error */
+tsa_long* tsa_long_create(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pair, int32_t rank, int32_t world,
+                          int32_t interval, int32_t group, int* status, char* err, size_t errcap);
+int tsa_long_ipc_export(const tsa_long* band, void* handle64);            /* cudaIpcGetMemHandle of the incoming boundary buffer */
+int tsa_long_ipc_connect(tsa_long* band, const void* handle64);           /* maps the next rank's buffer (cudaIpcOpenMemHandle) */
+int tsa_long_forward(tsa_long* band);
+int tsa_long_cost(const tsa_long* band, uint64_t* cost, int32_t* result_type);   /* last rank only */
+int tsa_long_owner(const tsa_long* band, int64_t column);                 /* rank whose band holds this column */
+int tsa_long_walk(tsa_long* band, tsa_long_walk_state* state, uint8_t* ops, size_t cap, size_t* n_ops);   /* unit ops, walk order */
+/* unit ops of all bands in walk order (last band first) -> run-length encoded result with the range of the pair */
+int tsa_long_result(const tsa_long* band, uint64_t cost, const uint8_t* ops_walk_order, size_t n_ops, tsa_result* out);
+void tsa_long_get_stats(const tsa_long* band, tsa_long_stats* stats);
+void tsa_long_dims(const tsa_long* band, int64_t* rows, int64_t* columns);
+void tsa_long_free(tsa_long* band);
+
 /* Integer roofline probe: measured issue rate (lanes/s) of the DPX add-min instructions on all SMs. */
 int tsa_measure_addmin_peak(int device, double* s16x2_lane_ops_per_s, double* s32_lane_ops_per_s);
 

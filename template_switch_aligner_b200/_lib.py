@@ -30,6 +30,8 @@ EXPORTS = [
     "tsa_config_parse", "tsa_config_default", "tsa_config_write", "tsa_config_free", "tsa_config_alphabet",
     "tsa_align_batch", "tsa_results_free", "tsa_batch_create", "tsa_batch_run", "tsa_batch_fetch", "tsa_batch_stats",
     "tsa_batch_free", "tsa_batch_timing", "tsa_batch_work", "tsa_measure_addmin_peak", "tsa_postprocess", "tsa_post_move", "tsa_device_count", "tsa_version",
+    "tsa_align_long", "tsa_long_create", "tsa_long_ipc_export", "tsa_long_ipc_connect", "tsa_long_forward", "tsa_long_cost", "tsa_long_owner",
+    "tsa_long_walk", "tsa_long_result", "tsa_long_get_stats", "tsa_long_dims", "tsa_long_free",
 ]
 
 
@@ -62,6 +64,15 @@ class TsaError(RuntimeError):
     def __init__(self, status, message=""):
         self.status = status
         super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+
+
+class TsaLongStats(C.Structure):
+    _fields_ = [("forward_ms", C.c_double), ("trace_ms", C.c_double), ("tiles", C.c_int64), ("tile_cells", C.c_int64),
+                ("boundary_bytes_out", C.c_int64), ("resident_bytes", C.c_int64), ("interval", C.c_int32), ("group", C.c_int32)]
+
+
+class TsaLongWalkState(C.Structure):
+    _fields_ = [("i", C.c_int32), ("j", C.c_int32), ("g", C.c_int32), ("need", C.c_int32), ("cost", C.c_int64), ("status", C.c_int32), ("reserved", C.c_int32)]
 
 
 def bind(cdll):
@@ -101,6 +112,31 @@ def bind(cdll):
     cdll.tsa_post_move.restype = C.c_int
     cdll.tsa_post_move.argtypes = [C.c_void_p, C.POINTER(TsaPair), C.c_int, C.POINTER(TsaOp), C.POINTER(C.c_size_t), C.c_size_t, C.c_int64, C.c_int64,
                                    C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+    cdll.tsa_align_long.restype = C.c_int
+    cdll.tsa_align_long.argtypes = [C.c_void_p, C.POINTER(TsaOptions), C.POINTER(TsaPair), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32,
+                                    C.POINTER(TsaResult), C.POINTER(TsaLongStats), C.c_char_p, C.c_size_t]
+    cdll.tsa_long_create.restype = C.c_void_p
+    cdll.tsa_long_create.argtypes = [C.c_void_p, C.POINTER(TsaOptions), C.POINTER(TsaPair), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
+    cdll.tsa_long_ipc_export.restype = C.c_int
+    cdll.tsa_long_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    cdll.tsa_long_ipc_connect.restype = C.c_int
+    cdll.tsa_long_ipc_connect.argtypes = [C.c_void_p, C.c_void_p]
+    cdll.tsa_long_forward.restype = C.c_int
+    cdll.tsa_long_forward.argtypes = [C.c_void_p]
+    cdll.tsa_long_cost.restype = C.c_int
+    cdll.tsa_long_cost.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+    cdll.tsa_long_owner.restype = C.c_int
+    cdll.tsa_long_owner.argtypes = [C.c_void_p, C.c_int64]
+    cdll.tsa_long_walk.restype = C.c_int
+    cdll.tsa_long_walk.argtypes = [C.c_void_p, C.POINTER(TsaLongWalkState), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    cdll.tsa_long_result.restype = C.c_int
+    cdll.tsa_long_result.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(TsaResult)]
+    cdll.tsa_long_get_stats.restype = None
+    cdll.tsa_long_get_stats.argtypes = [C.c_void_p, C.POINTER(TsaLongStats)]
+    cdll.tsa_long_dims.restype = None
+    cdll.tsa_long_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    cdll.tsa_long_free.restype = None
+    cdll.tsa_long_free.argtypes = [C.c_void_p]
     cdll.tsa_device_count.restype = C.c_int
     cdll.tsa_device_count.argtypes = []
     cdll.tsa_version.restype = C.c_char_p

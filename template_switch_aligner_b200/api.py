@@ -439,3 +439,129 @@ class StagedBatch:
 
     def __del__(self):
         self.close()
+
+
+# ---- one very long pair without template switches, column-banded over several GPUs (tsa_align_long / tsa_long_*) ------------------
+def _long_stats(s) -> dict:
+    return {"forward_ms": s.forward_ms, "trace_ms": s.trace_ms, "tiles": s.tiles, "tile_cells": s.tile_cells,
+            "boundary_bytes_out": s.boundary_bytes_out, "resident_bytes": s.resident_bytes, "interval": s.interval, "group": s.group}
+
+
+def align_long(aligner: Aligner, reference, query, *, devices: Optional[Sequence[int]] = None, interval: int = 0, group: int = 0,
+               rng=None, cost_limit: Optional[int] = None, memory_limit: Optional[int] = None, postprocess: int = 0):
+    """One pair without template switches (aligner.no_ts), its query columns cut into one band per device of THIS process; the
+    boundary columns stream between the devices over NVLink peer stores.  `memory_limit` (bytes per device) bounds what is resident:
+    checkpoint rows / boundary columns and the codes of one tile instead of a code matrix.  Returns (BatchResult, [stats per band])."""
+    lib = aligner._lib
+    devices = list(devices) if devices else [aligner.device]
+    arr, keep = _make_pairs([(reference, query, rng)])
+    res = (TsaResult * 1)()
+    stats = (_lib.TsaLongStats * len(devices))()
+    devs = (C.c_int32 * len(devices))(*devices)
+    err = C.create_string_buffer(512)
+    opt = _options(aligner.no_ts, devices[0], cost_limit, memory_limit, traceback=aligner.traceback, postprocess=postprocess, **aligner._strategy_kwargs())
+    rc = lib.tsa_align_long(aligner.config._h, C.byref(opt), arr, devs, len(devices), interval, group, res, stats, err, len(err))
+    if rc != 0:
+        raise TsaError(rc, err.value.decode(errors="replace"))
+    del keep
+    return _copy_results(lib, res, 1)[0], [_long_stats(s) for s in stats]
+
+
+class LongBand:
+    """One band of a long pair in this process (rank `rank` of `world`; torchrun: one process per GPU).  See include/tsalign_b200.h."""
+
+    def __init__(self, aligner: Aligner, reference, query, rank: int, world: int, *, interval: int = 0, group: int = 0, rng=None,
+                 memory_limit: Optional[int] = None, postprocess: int = 0):
+        self._lib = aligner._lib
+        self.rank, self.world = rank, world
+        arr, keep = _make_pairs([(reference, query, rng)])
+        status = C.c_int(0)
+        err = C.create_string_buffer(512)
+        opt = _options(aligner.no_ts, aligner.device, None, memory_limit, traceback=aligner.traceback, postprocess=postprocess, **aligner._strategy_kwargs())
+        self._h = self._lib.tsa_long_create(aligner.config._h, C.byref(opt), arr, rank, world, interval, group, C.byref(status), err, len(err))
+        if not self._h:
+            raise TsaError(status.value, err.value.decode(errors="replace"))
+        rows, cols = C.c_int64(), C.c_int64()
+        self._lib.tsa_long_dims(self._h, C.byref(rows), C.byref(cols))
+        self.rows, self.columns = rows.value, cols.value
+
+    def export_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        rc = self._lib.tsa_long_ipc_export(self._h, buf)
+        if rc != 0:
+            raise TsaError(rc, "tsa_long_ipc_export")
+        return buf.raw
+
+    def connect(self, handle: bytes) -> None:
+        rc = self._lib.tsa_long_ipc_connect(self._h, C.create_string_buffer(handle, 64))
+        if rc != 0:
+            raise TsaError(rc, "tsa_long_ipc_connect (CUDA IPC between the ranks' devices)")
+
+    def forward(self) -> None:
+        rc = self._lib.tsa_long_forward(self._h)
+        if rc != 0:
+            raise TsaError(rc, "tsa_long_forward")
+
+    def cost(self):
+        c, t = C.c_uint64(), C.c_int32()
+        rc = self._lib.tsa_long_cost(self._h, C.byref(c), C.byref(t))
+        if rc != 0:
+            raise TsaError(rc, "tsa_long_cost")
+        return c.value, _lib.RESULT_NAMES[t.value]
+
+    def owner(self, column: int) -> int:
+        return self._lib.tsa_long_owner(self._h, column)
+
+    def walk(self, state: tuple):
+        """state = (i, j, g, need, cost); returns (state, status, unit ops in walk order as bytes)."""
+        st = _lib.TsaLongWalkState(state[0], state[1], state[2], state[3], state[4], 0, 0)
+        cap = self.rows + self.columns + 64
+        buf = C.create_string_buffer(cap)
+        n = C.c_size_t(0)
+        rc = self._lib.tsa_long_walk(self._h, C.byref(st), buf, cap, C.byref(n))
+        if rc != 0:
+            raise TsaError(rc, "tsa_long_walk")
+        return (st.i, st.j, st.g, st.need, st.cost), st.status, buf.raw[:n.value]
+
+    def result(self, cost: int, ops_walk_order: bytes) -> BatchResult:
+        res = (TsaResult * 1)()
+        rc = self._lib.tsa_long_result(self._h, cost, ops_walk_order, len(ops_walk_order), res)
+        if rc != 0:
+            raise TsaError(rc, "tsa_long_result")
+        return _copy_results(self._lib, res, 1)[0]
+
+    def stats(self) -> dict:
+        s = _lib.TsaLongStats()
+        self._lib.tsa_long_get_stats(self._h, C.byref(s))
+        return _long_stats(s)
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.tsa_long_free(h)
+
+    def __del__(self):
+        self.close()
+
+
+def run_long_bands(bands: Sequence[LongBand], exchange=None):
+    """Drives the protocol of LongBand over bands that all live in this process (tests; `exchange` is unused).  A multi-process
+    launch does the same steps with its own exchange of the 64-byte handles and of the walk state (bench.py --config c5)."""
+    world = len(bands)
+    for r in range(world - 1):
+        bands[r].connect(bands[r + 1].export_handle())
+    for b in bands:
+        b.forward()
+    cost, kind = bands[-1].cost()
+    if kind != "FoundTarget":
+        return None, kind
+    state, ops, r = (bands[-1].rows, bands[-1].columns, 0, 1, cost), b"", world - 1
+    while True:
+        state, status, seg = bands[r].walk(state)
+        ops += seg
+        if status == 1:
+            break
+        if status < 0:
+            raise TsaError(11, f"walk failed with status {status}")
+        r = bands[r].owner(state[1])
+    return bands[-1].result(cost, ops), kind

@@ -10,6 +10,7 @@
 
 #include "tsa_config.hpp"
 #include "tsa_engine.hpp"
+#include "tsa_long.hpp"
 #include "tsa_post.hpp"
 #include "tsa_rt.hpp"
 
@@ -504,6 +505,208 @@ const char* tsa_version(void) {
 #else
     return "tsalign_b200 0.1.0 (SIMT emulator, tests only)";
 #endif
+}
+
+}  // extern "C"
+
+// ---- one long pair without template switches, column-banded (tsa_long.hpp) ------------------------------------------------------
+namespace {
+
+// Encodes the pair and cuts out its alignment range.  Returns TSA_OK or the per-pair input error.
+int encode_long(const HostConfig& host, const tsa_pair* pair, Encoded& enc, std::string& msg) {
+    encode_pairs(host, pair, 1, enc);
+    if (enc.pair_status[0] != TSA_OK) { msg = enc.pair_msg[0]; return enc.pair_status[0]; }
+    return TSA_OK;
+}
+
+void long_stats_out(const BandStats& b, tsa_long_stats& o) {
+    o.forward_ms = b.forward_ms; o.trace_ms = b.trace_ms; o.tiles = b.tiles; o.tile_cells = b.tile_cells;
+    o.boundary_bytes_out = b.boundary_bytes_out; o.resident_bytes = b.resident_bytes; o.interval = b.interval; o.group = b.group;
+}
+
+// unit ops in path order -> tsa_result (run-length encoded), range of the pair
+void long_result(tsa_result& r, const PairView& pv, int status, long long cost, std::vector<uint8_t>&& ops_path_order, bool with_ops, const tsa_options& o) {
+    PairCost pc;
+    pc.status = status; pc.cost = cost; pc.layers = 0;
+    pc.trace_status = with_ops ? TRACE_OK : TRACE_SKIPPED;
+    pc.ops = std::move(ops_path_order);
+    fill_result(r, pc, o);
+    r.reference_offset = pv.ro; r.reference_limit = pv.rl; r.query_offset = pv.qo; r.query_limit = pv.ql;
+}
+
+}  // namespace
+
+struct tsa_long {
+    HostConfig host;
+    Encoded enc;
+    tsa_options opt;
+    BandPlan plan;
+    std::unique_ptr<LongPair> band;
+    void* mapped = nullptr;    // the next rank's boundary buffer (cudaIpcOpenMemHandle)
+};
+
+extern "C" {
+
+int tsa_align_long(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pair, const int32_t* devices, int32_t n_devices,
+                   int32_t interval, int32_t group, tsa_result* out, tsa_long_stats* stats, char* err, size_t errcap) try {
+    if (!cfg || !pair || !out || n_devices < 0 || n_devices > 64) { set_err(err, errcap, "null or invalid argument"); return TSA_ERR_ARGUMENT; }
+    const tsa_options o = opt ? *opt : default_options();
+    if (!o.no_ts) { set_err(err, errcap, "tsa_align_long aligns without template switches: set no_ts"); return TSA_ERR_UNSUPPORTED; }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<int> devs;
+    for (int k = 0; k < n_devices; k++) devs.push_back(devices ? devices[k] : k);
+    if (devs.empty()) devs.push_back(o.device);
+    const int count = tsa_device_count();
+    for (int d : devs) if (d < 0 || d >= std::max(1, count) || count == 0) {
+        set_err(err, errcap, count ? "invalid CUDA device index" : "no CUDA device available: tsalign_b200 has no CPU path");
+        return TSA_ERR_NO_DEVICE;
+    }
+    memset(out, 0, sizeof(*out));
+    Encoded enc;
+    std::string msg;
+    const int in_rc = encode_long(cfg->host, pair, enc, msg);
+    if (in_rc != TSA_OK) { out->status = in_rc; snprintf(out->message, sizeof(out->message), "%s", msg.c_str()); return TSA_OK; }
+    const PairView& pv = enc.views[0];
+    const int nn = pv.rl - pv.ro, mm = pv.ql - pv.qo;
+    const size_t limit = o.memory_limit == UINT64_MAX ? 0 : (size_t)o.memory_limit;
+    LongResult lr = align_long(cfg->host, devs.data(), (int)devs.size(), pv.ref + pv.ro, nn, pv.qry + pv.qo, mm, interval, group, limit, o.no_traceback == 0);
+    if (lr.memory_limit_hit) {
+        out->status = TSA_OK; out->result_type = TSA_EXCEEDED_MEMORY_LIMIT; out->cost = 0;
+        snprintf(out->message, sizeof(out->message), "%s", lr.message.c_str());
+        out->reference_offset = pv.ro; out->reference_limit = pv.rl; out->query_offset = pv.qo; out->query_limit = pv.ql;
+    } else {
+        long_result(*out, pv, lr.status, lr.cost, std::move(lr.ops), o.no_traceback == 0, o);
+        postprocess_result(cfg->host, pv, o.postprocess, *out);
+    }
+    if (stats) for (size_t k = 0; k < lr.stats.size() && k < (size_t)n_devices; k++) long_stats_out(lr.stats[k], stats[k]);
+    out->duration_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return TSA_OK;
+} catch (const std::exception& e) {
+    set_err(err, errcap, e.what());
+    return TSA_ERR_INTERNAL;
+}
+
+tsa_long* tsa_long_create(const tsa_config* cfg, const tsa_options* opt, const tsa_pair* pair, int32_t rank, int32_t world,
+                          int32_t interval, int32_t group, int* status, char* err, size_t errcap) try {
+    int dummy; if (!status) status = &dummy;
+    if (!cfg || !pair || rank < 0 || world < 1 || rank >= world) { *status = TSA_ERR_ARGUMENT; set_err(err, errcap, "null or invalid argument"); return nullptr; }
+    std::unique_ptr<tsa_long> b(new tsa_long);
+    b->opt = opt ? *opt : default_options();
+    b->host = cfg->host;
+    if (!b->opt.no_ts) { *status = TSA_ERR_UNSUPPORTED; set_err(err, errcap, "column bands align without template switches: set no_ts"); return nullptr; }
+    std::string msg;
+    const int in_rc = encode_long(cfg->host, pair, b->enc, msg);
+    if (in_rc != TSA_OK) { *status = in_rc; set_err(err, errcap, msg); return nullptr; }
+    const PairView& pv = b->enc.views[0];
+    const int nn = pv.rl - pv.ro, mm = pv.ql - pv.qo;
+    const size_t limit = b->opt.memory_limit == UINT64_MAX ? 0 : (size_t)b->opt.memory_limit;
+    b->plan = plan_bands(nn, mm, world, interval, group, limit, b->opt.no_traceback == 0);
+    if (!b->plan.ok) { *status = TSA_ERR_UNSUPPORTED; set_err(err, errcap, b->plan.why); return nullptr; }
+    b->band.reset(new LongPair(cfg->host, b->opt.device, pv.ref + pv.ro, pv.qry + pv.qo, b->plan, rank, b->opt.no_traceback == 0));
+    if (!b->band->ok()) {
+        *status = b->band->error().find("CUDA") != std::string::npos ? TSA_ERR_NO_DEVICE : TSA_ERR_UNSUPPORTED;
+        set_err(err, errcap, b->band->error());
+        return nullptr;
+    }
+    *status = TSA_OK;
+    return b.release();
+} catch (const std::exception& e) {
+    if (status) *status = TSA_ERR_INTERNAL;
+    set_err(err, errcap, e.what());
+    return nullptr;
+}
+
+int tsa_long_ipc_export(const tsa_long* b, void* handle64) {
+    if (!b || !handle64) return TSA_ERR_ARGUMENT;
+#ifndef TSA_EMUL
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    if (cudaSetDevice(b->band->device()) != cudaSuccess || cudaIpcGetMemHandle(&h, b->band->incoming_boundary()) != cudaSuccess) { cudaGetLastError(); return TSA_ERR_INTERNAL; }
+    memcpy(handle64, &h, 64);
+#else
+    void* p = b->band->incoming_boundary();   // one process: the "handle" is the pointer
+    memset(handle64, 0, 64); memcpy(handle64, &p, sizeof(p));
+#endif
+    return TSA_OK;
+}
+
+int tsa_long_ipc_connect(tsa_long* b, const void* handle64) {
+    if (!b || !handle64) return TSA_ERR_ARGUMENT;
+#ifndef TSA_EMUL
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    if (cudaSetDevice(b->band->device()) != cudaSuccess || cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return TSA_ERR_INTERNAL; }
+    b->mapped = p;
+#else
+    void* p = nullptr; memcpy(&p, handle64, sizeof(p));
+#endif
+    b->band->set_outgoing_boundary(p);
+    return TSA_OK;
+}
+
+int tsa_long_forward(tsa_long* b) try {
+    if (!b) return TSA_ERR_ARGUMENT;
+    b->band->forward_launch();
+    b->band->forward_wait();
+    return TSA_OK;
+} catch (const std::exception& e) {
+    fprintf(stderr, "tsalign_b200: %s\n", e.what());
+    return TSA_ERR_INTERNAL;
+}
+
+int tsa_long_cost(const tsa_long* b, uint64_t* cost, int32_t* result_type) {
+    if (!b || !b->band->has_target()) return TSA_ERR_ARGUMENT;
+    const long long c = b->band->cost();
+    if (result_type) *result_type = c >= INF32 ? TSA_NO_TARGET : TSA_FOUND_TARGET;
+    if (cost) *cost = (uint64_t)c;
+    if (c < INF32 && b->band->saturated() && c >= (1 << 26) - 1) return TSA_ERR_UNSUPPORTED;
+    return TSA_OK;
+}
+
+int tsa_long_owner(const tsa_long* b, int64_t column) { return (!b || column < 0) ? -1 : b->plan.owner_of_column((int)column); }
+
+int tsa_long_walk(tsa_long* b, tsa_long_walk_state* state, uint8_t* ops, size_t cap, size_t* n_ops) try {
+    if (!b || !state || !n_ops) return TSA_ERR_ARGUMENT;
+    BandWalk in;
+    in.i = state->i; in.j = state->j; in.g = state->g; in.need = state->need; in.cost = state->cost; in.status = 0;
+    std::vector<uint8_t> rev;
+    const BandWalk st = b->band->walk(in, rev);
+    state->i = st.i; state->j = st.j; state->g = st.g; state->need = st.need; state->cost = st.cost; state->status = st.status;
+    *n_ops = rev.size();
+    if (rev.size() > cap || (!ops && !rev.empty())) return TSA_ERR_ARGUMENT;
+    if (!rev.empty()) memcpy(ops, rev.data(), rev.size());
+    return TSA_OK;
+} catch (const std::exception& e) {
+    fprintf(stderr, "tsalign_b200: %s\n", e.what());
+    return TSA_ERR_INTERNAL;
+}
+
+int tsa_long_result(const tsa_long* b, uint64_t cost, const uint8_t* ops_walk_order, size_t n_ops, tsa_result* out) try {
+    if (!b || !out || (!ops_walk_order && n_ops)) return TSA_ERR_ARGUMENT;
+    std::vector<uint8_t> path(n_ops);
+    for (size_t k = 0; k < n_ops; k++) path[k] = ops_walk_order[n_ops - 1 - k];
+    const PairView& pv = b->enc.views[0];
+    long_result(*out, pv, PAIR_OK, (long long)cost, std::move(path), true, b->opt);
+    postprocess_result(b->host, pv, b->opt.postprocess, *out);
+    return TSA_OK;
+} catch (const std::exception&) {
+    return TSA_ERR_INTERNAL;
+}
+
+void tsa_long_get_stats(const tsa_long* b, tsa_long_stats* stats) { if (b && stats) long_stats_out(b->band->stats(), *stats); }
+void tsa_long_dims(const tsa_long* b, int64_t* rows, int64_t* columns) {
+    if (!b) return;
+    if (rows) *rows = b->plan.nn;
+    if (columns) *columns = b->plan.mm;
+}
+
+void tsa_long_free(tsa_long* b) {
+    if (!b) return;
+#ifndef TSA_EMUL
+    if (b->mapped) { cudaSetDevice(b->band->device()); cudaIpcCloseMemHandle(b->mapped); }
+#endif
+    delete b;
 }
 
 }  // extern "C"

@@ -1,0 +1,328 @@
+// tsa_long.cu -- see tsa_long.hpp.  Compiled by nvcc for sm_100a (product) or by g++ with -DTSA_EMUL (tests/emul only).
+#include "tsa_long.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+
+#include "tsa_band.cuh"
+#include "tsa_engine.hpp"
+
+namespace tsa {
+
+namespace {
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) { if (bytes > cap) { rt::dev_free(p); p = rt::dev_alloc(bytes); cap = bytes; } }
+    ~Buf() { rt::dev_free(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+constexpr long long SMALL_INTS = 16;   // [0] ticket, [2..3] result, [4] ops_len, [8..] WalkState
+}  // namespace
+
+int BandPlan::owner_of_column(int j) const {
+    const int gi = (j < 0 ? 0 : j / WAVE_SW) / group;
+    int r = (int)(((long long)gi + 1) * world / n_groups);   // first guess, then correct
+    r = std::min(std::max(r, 0), world - 1);
+    while (r > 0 && group_first(r) > gi) r--;
+    while (r + 1 < world && group_first(r + 1) <= gi) r++;
+    return r;
+}
+
+long long BandPlan::resident_bytes(int rank, bool traceback) const {
+    const long long strips = strip_last(rank) - strip_first(rank) + 1;
+    const long long bw = std::min<long long>((long long)(strip_last(rank) + 1) * WAVE_SW, (long long)mm + 1) - (long long)strip_first(rank) * WAVE_SW;
+    long long b = (long long)nn + mm + 4096 + sizeof(DevConfig);                       // sequences, config
+    b += ((long long)nn + 1) * 8;                                                       // boundary between the strips of a group
+    const long long groups = (strips + group - 1) / group;
+    if (traceback) {
+        b += groups * ((long long)nn + 1) * 8;                                          // boundary column entering every group
+        b += (long long)(nn / interval) * (bw + 1) * 12;                                // checkpoint rows
+        b += ((long long)interval + 1) * (long long)group * WAVE_SW;                    // codes of one tile
+        b += (long long)nn + mm + 64;                                                   // unit ops
+    } else {
+        b += ((long long)nn + 1) * 8;                                                   // incoming boundary only
+    }
+    return b;
+}
+
+BandPlan plan_bands(int nn, int mm, int world, int interval, int group, size_t memory_limit, bool traceback) {
+    BandPlan best;
+    best.nn = nn; best.mm = mm; best.world = world;
+    best.s_total = wave_strips(mm + 1);
+    if (world < 1 || best.s_total < world) { best.why = "fewer 256-column strips than devices"; return best; }
+    // candidates: the given values, or the grid of powers of two; among those that fit the limit on every rank the one whose
+    // traceback recomputes the fewest cells (a path crosses ~nn / interval + columns / (256 group) tiles of interval x 256 group cells)
+    std::vector<int> cand_i, cand_g;
+    if (interval > 0) cand_i.push_back(interval); else for (int v = 256; v <= 16384; v <<= 1) cand_i.push_back(v);
+    const int g_cap = std::max(1, best.s_total / world);
+    if (group > 0) cand_g.push_back(std::min(group, g_cap)); else for (int v = 1; v <= 64; v <<= 1) if (v <= g_cap) cand_g.push_back(v);
+    double best_score = -1;
+    for (int ci : cand_i) for (int cg : cand_g) {
+        BandPlan p = best;
+        p.interval = ci; p.group = cg;
+        p.n_groups = (p.s_total + cg - 1) / cg;
+        if (p.n_groups < world) continue;
+        long long worst = 0;
+        for (int r = 0; r < world; r++) worst = std::max(worst, p.resident_bytes(r, traceback));
+        if (memory_limit && (unsigned long long)worst > memory_limit) continue;
+        // time model of the traceback (measured on a B200, profiles/r02_c5_*): a path crosses ~nn / interval + columns / (256 group)
+        // tiles; a tile costs a fixed host round trip plus the wavefront latency of its rows and of its pipeline of strips
+        const double tiles = (double)nn / ci + (double)mm / ((double)cg * WAVE_SW) + world;
+        const double t_tile = 120.0 + std::max(0.16 * ((double)ci + 32.0 * cg), (double)ci * cg * WAVE_SW / 4.0e5);   // microseconds
+        const double score = tiles * t_tile;
+        if (best_score < 0 || score < best_score) { best_score = score; p.ok = true; best = p; }
+    }
+    if (!best.ok) best.why = "no checkpoint spacing fits the memory limit";
+    return best;
+}
+
+struct LongPair::Impl {
+    cudaStream_t stream = 0;
+    Buf cfg, R, Q, colck, bnd_local, ckpt, tile, ops, small;
+    WaveBnd* bnd_out = nullptr;
+    int s_first = 0, s_last = 0, g_first = 0, n_groups = 0, bw = 0;
+    long long ckpt_stride = 0, dstride = 0;
+    int resident_blocks = 1;
+    size_t ops_cap = 0;
+#ifndef TSA_EMUL
+    cudaEvent_t ev[2];
+#endif
+};
+
+LongPair::LongPair(const HostConfig& cfg, int device, const uint8_t* R, const uint8_t* Q, const BandPlan& plan, int rank, bool traceback)
+    : impl_(new Impl), plan_(plan), device_(device), rank_(rank), traceback_(traceback) {
+    Impl& I = *impl_;
+    if (!plan.ok) { err_ = plan.why; return; }
+    if (!flatten_config(cfg, dev_, lc_, err_)) return;
+#ifndef TSA_EMUL
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { err_ = "no CUDA device available: tsalign_b200 has no CPU path"; return; }
+    if (device < 0 || device >= count) { err_ = "invalid CUDA device index"; return; }
+    rt::check(cudaSetDevice(device), "cudaSetDevice");
+    rt::check(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : I.ev) rt::check(cudaEventCreate(&e), "cudaEventCreate");
+    {
+        cudaDeviceProp prop;
+        rt::check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+        int per_sm = 0;
+        rt::check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_affine_band<true>, 32 * WAVE_WARPS, (size_t)WAVE_SMEM_INTS * sizeof(int)), "occupancy");
+        I.resident_blocks = std::max(1, per_sm) * prop.multiProcessorCount;
+    }
+#else
+    I.resident_blocks = 2;
+#endif
+    const int nn = plan.nn, mm = plan.mm;
+    I.s_first = plan.strip_first(rank); I.s_last = plan.strip_last(rank);
+    I.g_first = plan.group_first(rank); I.n_groups = plan.group_first(rank + 1) - I.g_first;
+    col_first_ = I.s_first * WAVE_SW;
+    I.bw = std::min((I.s_last + 1) * WAVE_SW, mm + 1) - col_first_;
+    I.cfg.ensure(sizeof(DevConfig));
+    I.R.ensure((size_t)nn + 16); I.Q.ensure((size_t)mm + 16);
+    rt::h2d(I.cfg.p, &dev_, sizeof(DevConfig), I.stream);
+    if (nn) rt::h2d(I.R.p, R, (size_t)nn, I.stream);
+    if (mm) rt::h2d(I.Q.p, Q, (size_t)mm, I.stream);
+    const size_t col_bytes = (size_t)(nn + 1) * 8;
+    I.bnd_local.ensure(col_bytes);
+    I.colck.ensure(col_bytes * (size_t)(traceback ? I.n_groups : 1));
+    I.small.ensure(SMALL_INTS * 4 + sizeof(WalkState));
+    if (traceback) {
+        I.ckpt_stride = ((long long)I.bw + 1) * 3;
+        I.ckpt.ensure((size_t)std::max(1, nn / plan.interval) * (size_t)I.ckpt_stride * 4);
+        I.dstride = (long long)plan.group * WAVE_SW;
+        I.tile.ensure((size_t)(plan.interval + 1) * (size_t)I.dstride);
+        I.ops_cap = (size_t)nn + mm + 64;
+        I.ops.ensure(I.ops_cap);
+    }
+    // boundary entries start as "not written" (tag 4095); the rank on the left may start writing as soon as every rank is built
+    rt::dev_memset(I.colck.p, 0xff, I.colck.cap, I.stream);
+    rt::dev_memset(I.bnd_local.p, 0xff, col_bytes, I.stream);
+    rt::stream_sync(I.stream);
+    stats_.resident_bytes = (long long)(I.cfg.cap + I.R.cap + I.Q.cap + I.bnd_local.cap + I.colck.cap + I.small.cap + I.ckpt.cap + I.tile.cap + I.ops.cap);
+    stats_.interval = plan.interval; stats_.group = plan.group;
+    ok_ = true;
+}
+
+LongPair::~LongPair() {
+#ifndef TSA_EMUL
+    if (impl_->stream) {
+        cudaSetDevice(device_);
+        for (auto& e : impl_->ev) cudaEventDestroy(e);
+        cudaStreamDestroy(impl_->stream);
+    }
+#endif
+    delete impl_;
+}
+
+void* LongPair::incoming_boundary() const { return impl_->colck.p; }
+void LongPair::set_outgoing_boundary(void* remote) { impl_->bnd_out = static_cast<WaveBnd*>(remote); }
+
+void LongPair::forward_launch() {
+    Impl& I = *impl_;
+#ifndef TSA_EMUL
+    rt::check(cudaSetDevice(device_), "cudaSetDevice");
+#endif
+    int init[SMALL_INTS] = {0};
+    init[2] = INF32;
+    rt::h2d(I.small.p, init, sizeof(init), I.stream);
+    rt::stream_sync(I.stream);   // `init` is a local
+    BandArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.R = I.R.as<uint8_t>(); ba.Q = I.Q.as<uint8_t>(); ba.nn = plan_.nn; ba.mm = plan_.mm;
+    ba.s_lo = I.s_first; ba.n_strips = I.s_last - I.s_first + 1; ba.s_total = plan_.s_total; ba.s_band_first = I.s_first; ba.s_band_last = I.s_last;
+    ba.group = traceback_ ? plan_.group : (1 << 30);   // costs only: no boundary column but the incoming one is kept
+    ba.row0 = 0; ba.row1 = plan_.nn;
+    ba.ck_col0 = col_first_;
+    ba.ckpt_in = nullptr; ba.ckpt_out = traceback_ ? I.ckpt.as<int>() : nullptr;
+    ba.interval = plan_.interval; ba.ckpt_stride = I.ckpt_stride;
+    ba.colck = I.colck.as<WaveBnd>(); ba.colck_g0 = traceback_ ? I.g_first : 0; ba.store_cols = traceback_ ? 1 : 0;
+    ba.bnd_local = I.bnd_local.as<WaveBnd>(); ba.bnd_out = I.bnd_out;
+    ba.dir = nullptr; ba.dstride = 0; ba.row_base = 0;
+    ba.ticket = I.small.as<int>(); ba.result = I.small.as<int>() + 2;
+    const int blocks = std::min(I.resident_blocks, (ba.n_strips + WAVE_WARPS - 1) / WAVE_WARPS);
+#ifndef TSA_EMUL
+    rt::check(cudaEventRecord(I.ev[0], I.stream), "cudaEventRecord");
+#endif
+    TSA_LAUNCH(k_affine_band<false>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), (size_t)WAVE_SMEM_INTS * sizeof(int), I.stream, I.cfg.as<DevConfig>(), ba);
+#ifndef TSA_EMUL
+    rt::check(cudaEventRecord(I.ev[1], I.stream), "cudaEventRecord");
+#endif
+    if (I.bnd_out) stats_.boundary_bytes_out = ((long long)plan_.nn + 1) * 8;
+}
+
+void LongPair::forward_wait() {
+    Impl& I = *impl_;
+#ifndef TSA_EMUL
+    rt::check(cudaSetDevice(device_), "cudaSetDevice");
+    rt::check(cudaEventSynchronize(I.ev[1]), "forward pass");
+    float ms = 0; cudaEventElapsedTime(&ms, I.ev[0], I.ev[1]);
+    stats_.forward_ms = ms;
+#endif
+    int h[SMALL_INTS];
+    rt::d2h(h, I.small.p, sizeof(h), I.stream);
+    rt::stream_sync(I.stream);
+    saturated_ = h[3] != 0;
+    if (has_target()) cost_ = h[2];
+}
+
+BandWalk LongPair::walk(const BandWalk& in, std::vector<uint8_t>& ops_rev) {
+    Impl& I = *impl_;
+    BandWalk st = in;
+    if (!traceback_) { st.status = WALK_ERR; return st; }
+#ifndef TSA_EMUL
+    rt::check(cudaSetDevice(device_), "cudaSetDevice");
+#endif
+    const auto t0 = std::chrono::steady_clock::now();
+    const int nn = plan_.nn, mm = plan_.mm, IV = plan_.interval, G = plan_.group;
+    size_t pos = 0;
+    while (st.status == WALK_GOING && st.j >= col_first_) {
+        const int k = st.i == 0 ? 0 : (st.i - 1) / IV;
+        const int row0 = k * IV, row1 = st.i;
+        const int s_hi = st.j / WAVE_SW, s_lo = (s_hi / G) * G;
+        if (s_hi > I.s_last || s_lo < I.s_first) { st.status = WALK_ERR; break; }
+        int init[SMALL_INTS] = {0};
+        WalkState ws;
+        ws.i = st.i; ws.j = st.j; ws.g = st.g; ws.need = st.need; ws.cost = st.cost; ws.status = WALK_GOING; ws.pad = 0;
+        rt::h2d(I.small.p, init, sizeof(init), I.stream);
+        rt::h2d(I.small.as<int>() + SMALL_INTS, &ws, sizeof(ws), I.stream);
+        rt::dev_memset(I.bnd_local.as<WaveBnd>() + row0, 0xff, (size_t)(row1 - row0 + 1) * 8, I.stream);
+        BandArgs ba;
+        memset(&ba, 0, sizeof(ba));
+        ba.R = I.R.as<uint8_t>(); ba.Q = I.Q.as<uint8_t>(); ba.nn = nn; ba.mm = mm;
+        ba.s_lo = s_lo; ba.n_strips = s_hi - s_lo + 1; ba.s_total = plan_.s_total; ba.s_band_first = I.s_first; ba.s_band_last = I.s_last;
+        ba.group = G; ba.row0 = row0; ba.row1 = row1; ba.ck_col0 = col_first_;
+        ba.ckpt_in = k > 0 ? I.ckpt.as<int>() + (long long)(k - 1) * I.ckpt_stride : nullptr;
+        ba.ckpt_out = nullptr; ba.interval = IV; ba.ckpt_stride = I.ckpt_stride;
+        ba.colck = I.colck.as<WaveBnd>(); ba.colck_g0 = I.g_first; ba.store_cols = 0;
+        ba.bnd_local = I.bnd_local.as<WaveBnd>(); ba.bnd_out = nullptr;
+        ba.dir = I.tile.as<uint8_t>(); ba.dstride = I.dstride; ba.row_base = k > 0 ? row0 + 1 : 0;
+        ba.ticket = I.small.as<int>(); ba.result = I.small.as<int>() + 2;
+        const int blocks = std::min(I.resident_blocks, (ba.n_strips + WAVE_WARPS - 1) / WAVE_WARPS);
+        TSA_LAUNCH(k_affine_band<true>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), (size_t)WAVE_SMEM_INTS * sizeof(int), I.stream, I.cfg.as<DevConfig>(), ba);
+        WalkArgs wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.R = ba.R; wa.Q = ba.Q; wa.dir = ba.dir; wa.dstride = ba.dstride; wa.row_base = ba.row_base; wa.col_base = s_lo * WAVE_SW;
+        wa.row_lo = row0;
+        wa.ops = I.ops.as<uint8_t>() + pos; wa.ops_cap = (int)std::min<size_t>(I.ops_cap - pos, (size_t)1 << 30);
+        wa.ops_len = I.small.as<int>() + 4;
+        wa.state = reinterpret_cast<WalkState*>(I.small.as<int>() + SMALL_INTS);
+        TSA_LAUNCH(k_band_walk, dim3(1), dim3(32), 0, I.stream, I.cfg.as<DevConfig>(), wa);
+        int h[SMALL_INTS];
+        rt::d2h(h, I.small.p, sizeof(h), I.stream);
+        rt::d2h(&ws, I.small.as<int>() + SMALL_INTS, sizeof(ws), I.stream);
+        rt::stream_sync(I.stream);
+        const bool moved = ws.i != st.i || ws.j != st.j || ws.need != st.need || ws.g != st.g || ws.status != WALK_GOING;
+        st.i = ws.i; st.j = ws.j; st.g = ws.g; st.need = ws.need; st.cost = ws.cost; st.status = ws.status;
+        pos += (size_t)h[4];
+        stats_.tiles++;
+        stats_.tile_cells += (long long)(row1 - row0 + 1) * (long long)ba.n_strips * WAVE_SW;
+        if (!moved) { st.status = WALK_ERR; break; }
+    }
+    if (pos) {
+        const size_t at = ops_rev.size();
+        ops_rev.resize(at + pos);
+        rt::d2h(ops_rev.data() + at, I.ops.p, pos, I.stream);
+        rt::stream_sync(I.stream);
+    }
+    stats_.trace_ms += 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return st;
+}
+
+LongResult align_long(const HostConfig& cfg, const int* devices, int n_devices, const uint8_t* R, int nn, const uint8_t* Q, int mm,
+                      int interval, int group, size_t memory_limit, bool traceback) {
+    LongResult res;
+    int world = std::max(1, n_devices);
+    // fewer strips than devices: use as many devices as there are strips
+    world = std::min(world, std::max(1, wave_strips(mm + 1)));
+    res.plan = plan_bands(nn, mm, world, interval, group, memory_limit, traceback);
+    if (!res.plan.ok) { res.status = PAIR_OK; res.memory_limit_hit = true; res.message = res.plan.why; return res; }
+    std::vector<std::unique_ptr<LongPair>> lp;
+    for (int r = 0; r < world; r++) {
+        lp.emplace_back(new LongPair(cfg, devices ? devices[r] : 0, R, Q, res.plan, r, traceback));
+        if (!lp.back()->ok()) throw std::runtime_error(lp.back()->error());
+    }
+#ifndef TSA_EMUL
+    for (int r = 0; r + 1 < world; r++) {
+        const int a = lp[r]->device(), b = lp[r + 1]->device();
+        if (a != b) {
+            int can = 0;
+            rt::check(cudaDeviceCanAccessPeer(&can, a, b), "cudaDeviceCanAccessPeer");
+            if (!can) throw std::runtime_error("devices of neighbouring bands have no peer access");
+            rt::check(cudaSetDevice(a), "cudaSetDevice");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rt::check(e, "cudaDeviceEnablePeerAccess");
+            cudaGetLastError();
+        }
+    }
+#endif
+    for (int r = 0; r + 1 < world; r++) lp[r]->set_outgoing_boundary(lp[r + 1]->incoming_boundary());
+    for (int r = 0; r < world; r++) lp[r]->forward_launch();
+    for (int r = 0; r < world; r++) lp[r]->forward_wait();
+    bool sat = false;
+    for (int r = 0; r < world; r++) sat = sat || lp[r]->saturated();
+    res.cost = lp[world - 1]->cost();
+    if (res.cost >= INF32) res.status = PAIR_NO_TARGET;
+    else if (sat && res.cost >= WAVE_SAT) res.status = PAIR_ERR_COST_RANGE;
+    if (res.status == PAIR_OK && traceback) {
+        BandWalk st;
+        st.i = nn; st.j = mm; st.g = 0; st.need = 1; st.cost = res.cost; st.status = WALK_GOING;
+        std::vector<uint8_t> rev;
+        rev.reserve((size_t)nn + mm);
+        int r = world - 1;
+        for (;;) {
+            st = lp[r]->walk(st, rev);
+            if (st.status != WALK_GOING) break;
+            r = st.j < 0 ? -1 : res.plan.owner_of_column(st.j);
+            if (r < 0) { st.status = WALK_ERR; break; }
+        }
+        if (st.status != WALK_DONE) throw std::runtime_error("long pair: the traceback walk failed (status " + std::to_string(st.status) + ")");
+        res.ops.assign(rev.rbegin(), rev.rend());
+    }
+    for (int r = 0; r < world; r++) res.stats.push_back(lp[r]->stats());
+    return res;
+}
+
+}  // namespace tsa

@@ -47,6 +47,7 @@ TSA_DEV uint32_t shfl_xor(uint32_t v, int d) { return __shfl_xor_sync(0xffffffff
 TSA_DEV uint32_t shfl_idx(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 TSA_DEV int reduce_min_s32(int v) { return __reduce_min_sync(0xffffffffu, v); }
 TSA_DEV int reduce_max_s32(int v) { return __reduce_max_sync(0xffffffffu, v); }
+TSA_DEV int reduce_add_s32(int v) { return __reduce_add_sync(0xffffffffu, v); }
 TSA_DEV uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 TSA_DEV void sync_warp() { __syncwarp(); }
 TSA_DEV void sync_block() { __syncthreads(); }
@@ -136,6 +137,15 @@ inline int reduce_min_s32(int v) {
     return r;
 }
 inline int reduce_max_s32(int v) { return -reduce_min_s32(-v); }
+inline int reduce_add_s32(int v) {
+    uint32_t* s = emu::warp_slots();
+    s[lane_id()] = (uint32_t)v;
+    emu::warp_barrier();
+    int r = 0;
+    for (int i = 0; i < 32; i++) r += (int)s[i];
+    emu::warp_barrier();
+    return r;
+}
 inline uint32_t ballot(bool p) {
     uint32_t* s = emu::warp_slots();
     s[lane_id()] = p ? 1u : 0u;
