@@ -551,7 +551,9 @@ void Engine::run_staged() {
             min_lw = std::min(min_lw, LW);
         }
         if (min_lw < (1 << 30)) {
-            const size_t bytes = std::max(one, std::min(want, (size_t)6 << 30)) + 4096;
+            size_t cap_bytes = (size_t)6 << 30;
+            if (const char* qm = getenv("TSA_B200_QUEUE_MB")) cap_bytes = std::max<size_t>(1, (size_t)atoll(qm)) << 20;   // developer knob: slice size of the split jump
+            const size_t bytes = std::max(one, std::min(want, cap_bytes)) + 4096;
             I.q_rows.ensure(bytes);
             I.q_hdr.ensure((I.q_rows.cap / ((size_t)min_lw * 4) + 1) * sizeof(QueueHdr));
             I.q_counts.ensure((size_t)MAX_Q_SLICES * 4);
@@ -560,7 +562,7 @@ void Engine::run_staged() {
     auto jump_split = [&](int c, int stage, long long& l) {
         Chunk ck = I.ck;
         const int LW = 32 * CLASS_C[c];
-        ck.q_cap = (int)std::min<size_t>(I.q_rows.cap / ((size_t)LW * 4), (size_t)1 << 30);
+        ck.q_cap = (int)std::min<size_t>(I.q_rows.cap / ((size_t)LW * 4), (size_t)1 << 30) & ~(QUEUE_RESERVE - 1);   // whole reservation blocks
         ck.q_hdr = I.q_hdr.as<QueueHdr>();
         ck.q_rows = I.q_rows.as<uint32_t>();
         const int slice_pairs = (int)std::max(1.0, std::min(65535.0, (double)ck.q_cap / (I.q_est[c] * 1.3)));

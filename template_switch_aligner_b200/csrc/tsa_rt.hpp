@@ -57,6 +57,14 @@ TSA_DEV int min3_s32(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 TSA_DEV uint32_t addmin_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
 TSA_DEV uint32_t min3_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }
 TSA_DEV uint32_t min_s16x2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+TSA_DEV uint32_t max_s16x2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+// per half: 0xffff where a + negb < 0 (a - b without overflow for the non-negative costs used here): VIADDMNMX + PRMT
+TSA_DEV uint32_t ltmask_s16x2(uint32_t a, uint32_t negb) {
+    uint32_t r;   // (__byte_perm ignores the sign-replication bit of the selector nibbles)
+    asm("prmt.b32 %0, %1, 0, 0xbb99;" : "=r"(r) : "r"(__viaddmin_s16x2(a, negb, 0x7fff7fffu)));
+    return r;
+}
+TSA_DEV int clamp0_s32(int v, int hi) { return __vimin_s32_relu(v, hi); }                            // max(min(v, hi), 0)
 TSA_DEV uint32_t add_s16x2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 TSA_DEV uint32_t cmplt_s16x2(uint32_t a, uint32_t b) { return __vcmplts2(a, b); }                 // per half: 0xffff where a < b (signed)
 TSA_DEV int atomic_min_s32(int* p, int v) { return atomicMin(p, v); }
@@ -65,6 +73,7 @@ TSA_DEV int atomic_max_s32(int* p, int v) { return atomicMax(p, v); }
 TSA_DEV int atomic_and_s32(int* p, int v) { return atomicAnd(p, v); }
 TSA_DEV int atomic_add_s32(int* p, int v) { return atomicAdd(p, v); }
 TSA_DEV int clz_u32(uint32_t v) { return __clz((int)v); }
+TSA_DEV int popc_u32(uint32_t v) { return __popc(v); }
 TSA_DEV int ffs_u32(uint32_t v) { return __ffs((int)v); }                                          // 1-based index of the lowest set bit, 0 if none
 // producer / consumer flags between warps of one launch (k_affine_wave): release store, acquire load, L2 data load
 TSA_DEV int ld_acquire_s32(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
@@ -170,6 +179,9 @@ inline uint32_t min3_s16x2(uint32_t a, uint32_t b, uint32_t c) {
     return pack16(std::min<int>(lo16(a), std::min<int>(lo16(b), lo16(c))), std::min<int>(hi16(a), std::min<int>(hi16(b), hi16(c))));
 }
 inline uint32_t min_s16x2(uint32_t a, uint32_t b) { return pack16(std::min<int>(lo16(a), lo16(b)), std::min<int>(hi16(a), hi16(b))); }
+inline uint32_t max_s16x2(uint32_t a, uint32_t b) { return pack16(std::max<int>(lo16(a), lo16(b)), std::max<int>(hi16(a), hi16(b))); }
+inline uint32_t ltmask_s16x2(uint32_t a, uint32_t negb) { return ((int16_t)(lo16(a) + lo16(negb)) < 0 ? 0xffffu : 0u) | ((int16_t)(hi16(a) + hi16(negb)) < 0 ? 0xffff0000u : 0u); }
+inline int clamp0_s32(int v, int hi) { return std::max(std::min(v, hi), 0); }
 inline uint32_t add_s16x2(uint32_t a, uint32_t b) { return pack16((int16_t)(lo16(a) + lo16(b)), (int16_t)(hi16(a) + hi16(b))); }
 inline uint32_t cmplt_s16x2(uint32_t a, uint32_t b) { return (lo16(a) < lo16(b) ? 0xffffu : 0u) | (hi16(a) < hi16(b) ? 0xffff0000u : 0u); }
 inline int atomic_min_s32(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
@@ -179,6 +191,7 @@ inline int atomic_and_s32(int* p, int v) { int o = *p; *p = o & v; return o; }
 inline int atomic_add_s32(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline int clz_u32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 inline int ffs_u32(uint32_t v) { return __builtin_ffs((int)v); }
+inline int popc_u32(uint32_t v) { return __builtin_popcount(v); }
 inline int ld_acquire_s32(const int* p) { return *(const volatile int*)p; }
 inline void st_release_s32(int* p, int v) { *(volatile int*)p = v; }
 inline int ld_cg_s32(const int* p) { return *(const volatile int*)p; }

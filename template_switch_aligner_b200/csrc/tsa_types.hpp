@@ -84,11 +84,12 @@ struct QueueHdr {
     int kk;                  // kind index | flags << 8 (bit 0 / 1: the low / high chain can still produce a seed below the bound); < 0: reserved slot that was not used
     int b;                   // pair
     int e0, ip;              // primary end of the low chain (the high chain ends at e0 + 1), entrance row
-    int lc0, lc1;            // length costs of the two chains at this row (INF32: no exit)
-    int rmD;                 // row minimum of D at the entrance row, clamped to 2^20
+    int nbw;                 // packed, negated pruning bounds of the two chains: -(slack - rowmin D(ip) - length cost), 0: no exit from this row
+    int lcw;                 // packed length costs of the two chains at this row (INF16: no exit)
+    int pad;
     int T;                   // pruning bound of the pair during this launch
 };
-constexpr int QUEUE_RESERVE = 4;   // slots a warp reserves per atomic
+constexpr int QUEUE_RESERVE = 8;   // slots a warp reserves per atomic: rows of one chain pair, evaluated by one warp of k_ts_eval
 
 // Everything a kernel needs about the resident chunk of pairs.
 struct Chunk {
