@@ -530,6 +530,7 @@ void Engine::run_staged() {
         rt::d2h(h, I.counters.p, sizeof(h), I.stream);
         rt::stream_sync(I.stream);
         stats_.chains_run += h[1]; stats_.rows_filled += h[2]; stats_.rows_jumped += h[3]; stats_.chains_started += h[4];
+        if (getenv("TSA_B200_DEBUG")) fprintf(stderr, "[tsalign_b200] layer: chains %d/%d rows %d queued %d dominated %d evaluated %d\n", h[1], h[4], h[2], h[5], h[6], h[3]);
         for (int c = 0; c < N_CLASS; c++) counts8[c] = h[8 + c];
     };
     // Row queue of the split jump (classes without column windows): sized from the learned demand per pair, at least the worst case

@@ -86,7 +86,7 @@ struct QueueHdr {
     int e0, ip;              // primary end of the low chain (the high chain ends at e0 + 1), entrance row
     int nbw;                 // packed, negated pruning bounds of the two chains: -(slack - rowmin D(ip) - length cost), 0: no exit from this row
     int lcw;                 // packed length costs of the two chains at this row (INF16: no exit)
-    int pad;
+    int msw;                 // packed cheapest start costs of the two chains at this row (lower bound of every jump-in)
     int T;                   // pruning bound of the pair during this launch
 };
 constexpr int QUEUE_RESERVE = 8;   // slots a warp reserves per atomic: rows of one chain pair, evaluated by one warp of k_ts_eval
