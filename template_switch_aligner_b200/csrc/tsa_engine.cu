@@ -181,7 +181,8 @@ struct Engine::Impl {
     DevBuf band, winflag;                             // column windows: band vectors of the fill, overflow flags
     DevBuf q_hdr, q_rows, q_counts;                   // row queue between the row kernel and the evaluation kernel
     size_t q_cap = 0;                                 // slots
-    double q_est[N_CLASS] = {0};                      // learned demand of queue slots per pair, by class (sizes the slices)
+    double q_est[N_CLASS][2][3] = {};                 // learned demand of queue slots per pair, by class, first / later deepening round and
+                                                      // layer (0, 1, 2+): the demand differs by an order of magnitude between them (sizes the slices)
     bool any_win = false;
     std::vector<int> h_winflag;
     DevBuf wave_prefix, wave_ticket;   // k_affine_wave: first ticket per pair, ticket counter
@@ -535,8 +536,9 @@ void Engine::run_staged() {
     };
     // Row queue of the split jump (classes without column windows): sized from the learned demand per pair, at least the worst case
     // of one pair (every row of every chain queued), at most 6 GiB.
-    int n_slices = 0;
+    int n_slices = 0, est_r = 0, est_l = 0;      // bucket of the learned demand the current layer uses
     std::vector<int> slice_size, slice_class, h_qcounts;
+    auto est = [&](int c) -> double& { return I.q_est[c][est_r][est_l]; };
     {
         size_t want = 0, one = 0;
         int min_lw = 1 << 30;
@@ -546,13 +548,16 @@ void Engine::run_staged() {
             const int n_ep = std::max(0, (mx - dev_.ml + 2) / 2);
             const double chains = (double)dev_.n_kinds * n_ep;
             const double rows_max = (double)std::min(dev_.lmax, mx) + 1 + QUEUE_RESERVE;
-            if (I.q_est[c] <= 0) I.q_est[c] = chains * 2.0;
+            for (auto& byround : I.q_est[c]) for (double& v : byround) if (v <= 0) v = chains * 2.0;
             one = std::max(one, (size_t)(chains * rows_max) * LW * 4);
-            want += (size_t)((double)I.class_list[c].size() * I.q_est[c] * 1.3) * LW * 4;
+            want += (size_t)((double)I.class_list[c].size() * I.q_est[c][0][0] * 1.3) * LW * 4;
             min_lw = std::min(min_lw, LW);
         }
         if (min_lw < (1 << 30)) {
-            size_t cap_bytes = (size_t)6 << 30;
+            size_t cap_bytes = (size_t)16 << 30;      // fewer, larger slices are faster (measured: 6 / 12 / 24 GiB)
+#ifndef TSA_EMUL
+            { size_t free_b = 0, total_b = 0; if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) cap_bytes = std::min(cap_bytes, std::max<size_t>((size_t)1 << 28, (free_b + I.q_rows.cap) / 4)); }
+#endif
             if (const char* qm = getenv("TSA_B200_QUEUE_MB")) cap_bytes = std::max<size_t>(1, (size_t)atoll(qm)) << 20;   // developer knob: slice size of the split jump
             const size_t bytes = std::max(one, std::min(want, cap_bytes)) + 4096;
             I.q_rows.ensure(bytes);
@@ -566,7 +571,7 @@ void Engine::run_staged() {
         ck.q_cap = (int)std::min<size_t>(I.q_rows.cap / ((size_t)LW * 4), (size_t)1 << 30) & ~(QUEUE_RESERVE - 1);   // whole reservation blocks
         ck.q_hdr = I.q_hdr.as<QueueHdr>();
         ck.q_rows = I.q_rows.as<uint32_t>();
-        const int slice_pairs = (int)std::max(1.0, std::min(65535.0, (double)ck.q_cap / (I.q_est[c] * 1.3)));
+        const int slice_pairs = (int)std::max(1.0, std::min(65535.0, (double)ck.q_cap / (est(c) * 1.3)));
         const int ml_ = dev_.ml, A_ = dev_.A, nk = dev_.n_kinds, mx = I.class_maxlen[c];
         int* counts = I.q_counts.as<int>();
         switch (c) {
@@ -619,12 +624,13 @@ void Engine::run_staged() {
             for (int s2 = 0; s2 < n_slices; s2++) {
                 const int c = slice_class[(size_t)s2];
                 const size_t cap = std::min<size_t>(I.q_rows.cap / ((size_t)32 * CLASS_C[c] * 4), (size_t)1 << 30);
-                I.q_est[c] = std::max(I.q_est[c], (double)h_qcounts[(size_t)s2] / std::max(1, slice_size[(size_t)s2]));
+                est(c) = std::max(est(c), (double)h_qcounts[(size_t)s2] / std::max(1, slice_size[(size_t)s2]));
                 if ((size_t)h_qcounts[(size_t)s2] > cap) {
                     overflow = true;
                     if (slice_size[(size_t)s2] == 1 || attempt > 8) throw std::runtime_error("row queue: one pair does not fit the queue");
                 }
             }
+            if (getenv("TSA_B200_DEBUG")) fprintf(stderr, "[tsalign_b200] jump layer: attempt %d, %d slices, overflow %d, q_est %.0f\n", attempt, n_slices, (int)overflow, est(1));
             if (!overflow) return;
         }
     };
@@ -652,6 +658,7 @@ void Engine::run_staged() {
                     TSA_LAUNCH(k_clear_seeds, dim3(clear_gx, (unsigned)cnt), dim3(256), 0, I.stream, I.ck, cur[c] + off, cnt);
                     stats_.launches++;
                 }
+            est_r = round > 0 ? 1 : 0; est_l = std::min(layer, 2);
             jump_layer();
             int* out = spare[which];
             for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) {
