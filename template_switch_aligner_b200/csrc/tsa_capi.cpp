@@ -143,6 +143,7 @@ void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
         }
         break;
     case PAIR_NO_TARGET: r.status = TSA_OK; r.result_type = TSA_NO_TARGET; break;
+    case PAIR_MEMORY_LIMIT: r.status = TSA_OK; r.result_type = TSA_EXCEEDED_MEMORY_LIMIT; snprintf(r.message, sizeof(r.message), "the pair alone needs more resident memory than --memory-limit"); break;
     case PAIR_ERR_TOO_LONG: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "template-switch column windows exceed 1056 columns at this cost threshold"); break;
     case PAIR_ERR_COST_RANGE: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "alignment cost exceeds the kernels' integer range (2^14 with template switches, else 2^26)"); break;
     case PAIR_ERR_LAYER_CAP: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "not proven optimal within max_template_switches template switches: refused"); break;
@@ -209,7 +210,7 @@ AlignOptions engine_options(const tsa_options& o) {
     a.no_windows = (o.reserved & 2) != 0;    // bit 1: developer knob, medium pairs skip the column-window stage
     a.test_small_windows = (o.reserved & 4) != 0;   // bit 2: honoured by emulator builds only
     if (a.traceback) a.max_layers = std::min(a.max_layers, (int)MAX_TRACE_LAYERS);
-    if (o.memory_limit != UINT64_MAX) a.chunk_bytes = (size_t)std::max<uint64_t>(o.memory_limit, (uint64_t)1 << 20);
+    if (o.memory_limit != UINT64_MAX) { a.chunk_bytes = (size_t)std::max<uint64_t>(o.memory_limit, (uint64_t)1 << 20); a.memory_limit_strict = true; }
     return a;
 }
 
@@ -219,6 +220,8 @@ tsa_options default_options() {
     o.cost_limit = UINT64_MAX; o.memory_limit = UINT64_MAX;
     return o;
 }
+
+void long_result(tsa_result& r, const PairView& pv, int status, long long cost, std::vector<uint8_t>&& ops_path_order, bool with_ops, const tsa_options& o);
 
 }  // namespace
 
@@ -412,7 +415,27 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
         out[i].status = enc.pair_status[i];
         snprintf(out[i].message, sizeof(out[i].message), "%s", enc.pair_msg[i].c_str());
     }
+    // --memory-limit without template switches: a pair whose code matrix does not fit is aligned by the checkpointed path of
+    // tsa_long.cu (checkpoint rows + recomputed tiles under the same limit): the limit bounds what is resident, the alignment is
+    // still produced; ExceededMemoryLimit only if not even the checkpoints fit.
+    std::vector<char> done(enc.live.size(), 0);
+    if (o.no_ts) for (size_t k = 0; k < enc.live.size(); k++) if (costs[k].status == PAIR_MEMORY_LIMIT) {
+        const PairView& pv = enc.views[k];
+        tsa_result& r = out[enc.live[k]];
+        const int dev = o.device;
+        LongResult lr = align_long(cfg->host, &dev, 1, pv.ref + pv.ro, pv.rl - pv.ro, pv.qry + pv.qo, pv.ql - pv.qo, 0, 0, (size_t)o.memory_limit, o.no_traceback == 0);
+        if (lr.memory_limit_hit) {
+            r.status = TSA_OK; r.result_type = TSA_EXCEEDED_MEMORY_LIMIT; r.cost = 0;
+            snprintf(r.message, sizeof(r.message), "%s", lr.message.c_str());
+            r.reference_offset = pv.ro; r.reference_limit = pv.rl; r.query_offset = pv.qo; r.query_limit = pv.ql;
+        } else {
+            long_result(r, pv, lr.status, lr.cost, std::move(lr.ops), o.no_traceback == 0, o);
+            postprocess_result(cfg->host, pv, o.postprocess, r);
+        }
+        done[k] = 1;
+    }
     parallel_for(enc.live.size(), [&](size_t k) {
+        if (done[k]) return;
         tsa_result& r = out[enc.live[k]];
         fill_result(r, costs[k], o);
         const PairView& pv = enc.views[k];

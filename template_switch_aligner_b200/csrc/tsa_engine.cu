@@ -900,14 +900,25 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
         budget = (size_t)1 << 30;
 #endif
     }
+    auto resident_bytes = [&](const PairView& p) {
+        const size_t cells = (size_t)(p.n + 1) * (p.m + 1);
+        size_t b = (!opt.no_ts && dev_.n_kinds > 0) ? bytes_per_pair(p.n, p.m) : (size_t)(p.n + p.m) * 20 + 512;
+        if (opt.traceback) b += cells * ((!opt.no_ts && dev_.n_kinds > 0) ? 9 : 1) + 3 * (size_t)(p.n + p.m) + 256;   // codes (+ D) of ~3 layers, ops
+        if (!opt.no_ts && dev_.n_kinds > 0 && (dev_.left_flank > 0 || dev_.right_flank > 0))   // flank planes, and their codes of ~4 layers
+            b += cells * (12 + (opt.traceback ? (size_t)(dev_.left_flank + dev_.right_flank + 1) * 4 : 0));
+        return b;
+    };
     while (i < n) {
+        if (opt.memory_limit_strict && resident_bytes(pairs[i]) > budget) {
+            // generic_a_star/src/lib.rs:380-389: the search gives up when its store outgrows the limit.  (The C ABI re-runs pairs
+            // without template switches through the checkpointed path of tsa_long.cu, which needs no code matrix.)
+            out[i] = PairCost(); out[i].status = PAIR_MEMORY_LIMIT;
+            i++;
+            continue;
+        }
         size_t j = i, bytes = 0;
         while (j < n) {
-            const size_t cells = (size_t)(pairs[j].n + 1) * (pairs[j].m + 1);
-            size_t b = (!opt.no_ts && dev_.n_kinds > 0) ? bytes_per_pair(pairs[j].n, pairs[j].m) : (size_t)(pairs[j].n + pairs[j].m) * 20 + 512;
-            if (opt.traceback) b += cells * ((!opt.no_ts && dev_.n_kinds > 0) ? 9 : 1) + 3 * (size_t)(pairs[j].n + pairs[j].m) + 256;   // codes (+ D) of ~3 layers, ops
-            if (!opt.no_ts && dev_.n_kinds > 0 && (dev_.left_flank > 0 || dev_.right_flank > 0))   // flank planes, and their codes of ~4 layers
-                b += cells * (12 + (opt.traceback ? (size_t)(dev_.left_flank + dev_.right_flank + 1) * 4 : 0));
+            const size_t b = resident_bytes(pairs[j]);
             if (j > i && bytes + b > budget) break;
             bytes += b; j++;
         }

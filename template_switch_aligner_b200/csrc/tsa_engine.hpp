@@ -19,6 +19,7 @@ struct AlignOptions {
     bool no_windows = false;       // developer knob: pairs of 545..1055 characters skip the column-window stage (parity tests)
     bool test_small_windows = false;  // emulator builds only: pairs wider than 48 use 96 / 160-column windows (CPU tests of the window logic)
     size_t chunk_bytes = 0;        // HBM budget of one resident chunk of pairs; 0 = half of the free device memory
+    bool memory_limit_strict = false;   // --memory-limit given: a pair that does not fit the budget on its own is reported (PAIR_MEMORY_LIMIT), not staged
 };
 
 // One pair, already encoded as alphabet indices.
@@ -34,6 +35,7 @@ enum PairStatus {
     PAIR_ERR_TOO_LONG = 2,         // TS-enabled pair longer than the jump kernel's widest instantiation
     PAIR_ERR_COST_RANGE = 3,       // costs do not fit the packed s16 lanes of the jump kernel
     PAIR_ERR_LAYER_CAP = 4,        // still improving after max_layers template switches
+    PAIR_MEMORY_LIMIT = 6,         // AStarResult::ExceededMemoryLimit: the pair alone needs more than --memory-limit resident
     PAIR_ERR_FLANKS = 5,           // flank lengths > 0 with TS enabled: not built yet
 };
 

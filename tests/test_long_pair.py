@@ -98,3 +98,19 @@ def test_long_pair_matches_resident_codes_gpu(configs):
     assert ok and cost == res.cost and (er, eq) == (len(r), len(q))
     bands = [api.LongBand(aligner, r, q, k, 2, interval=2048, group=4) for k in range(2)]   # the per-rank protocol (CUDA IPC handles need two processes: bench_c5.py)
     del bands
+
+
+def test_batch_memory_limit_emulated(configs):
+    # --memory-limit on the batch entry point: a --no-ts pair whose code matrix does not fit is aligned by the checkpointed path
+    # (same cost, alignment rescored); with template switches the pair is reported as ExceededMemoryLimit (generic_a_star/src/lib.rs:380-389)
+    flat = oracle.FlatConfig(parse_config_any(configs["sample"]))
+    r, q = workloads.long_pair(21, 1300, sub_rate=0.05, indel_rate=0.02)
+    small = ("ACGTTGCA" * 10, "ACGTTGCA" * 10)
+    nots = tsa.Aligner(costs=configs["sample"], no_ts=True, lib=emul())
+    got = nots.align_batch([small, (r, q), small], memory_limit=1 << 20)
+    assert [g.result_type for g in got] == ["FoundTarget"] * 3
+    _check(flat, r, q, got[1])
+    _check(flat, small[0], small[1], got[0])
+    ts = tsa.Aligner(costs=configs["sample"], lib=emul())
+    got = ts.align_batch([small, (r[:400], q[:400]), small], memory_limit=1 << 20)
+    assert [g.result_type for g in got] == ["FoundTarget", "ExceededMemoryLimit", "FoundTarget"] and got[1].status == 0 and got[1].ops is None
