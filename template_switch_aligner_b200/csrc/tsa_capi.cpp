@@ -384,6 +384,7 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     auto t1 = std::chrono::steady_clock::now();
     std::vector<PairCost> costs(enc.views.size());
     const size_t live = enc.views.size();
+    auto run_engines = [&](const AlignOptions& ao, std::vector<PairCost>& costs) -> int {
 #ifndef TSA_EMUL
     const bool split = live >= 4096 && !o.no_ts;
 #else
@@ -396,8 +397,7 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
         Engine& second = *mcfg->engine2[slot];
         if (!second.ok()) { set_err(err, errcap, second.error()); mcfg->engine2[slot].reset(); return TSA_ERR_NO_DEVICE; }
         const size_t half = live / 2;
-        const AlignOptions ao = engine_options(o);
-        std::exception_ptr failed;
+                std::exception_ptr failed;
         std::thread other([&]() {
             try { second.align_costs(enc.views.data() + half, live - half, ao, costs.data() + half); }
             catch (...) { failed = std::current_exception(); }
@@ -407,7 +407,32 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
         other.join();
         if (failed) std::rethrow_exception(failed);
     } else {
-        engine.align_costs(enc.views.data(), live, engine_options(o), costs.data());
+        engine.align_costs(enc.views.data(), live, ao, costs.data());
+    }
+        return TSA_OK;
+    };
+    AlignOptions ao = engine_options(o);
+    if (o.descendant_strategy == 1 && !o.no_ts) {
+        // --ts-descendant-strategy allow-only-all-equal (strategies/descendant.rs:22-104): every template switch of an alignment has
+        // the same primary.  As an explicit state dimension that is the better of two searches, one with the kinds whose primary is
+        // the reference and one with the kinds whose primary is the query (ties: the reference).
+        std::vector<PairCost> other(costs.size());
+        ao.primary_filter = 1;
+        int rc1 = run_engines(ao, costs);
+        if (rc1 != TSA_OK) return rc1;
+        ao.primary_filter = 2;
+        rc1 = run_engines(ao, other);
+        if (rc1 != TSA_OK) return rc1;
+        for (size_t k = 0; k < costs.size(); k++) {
+            const auto is_err = [](const PairCost& p) { return p.status != PAIR_OK && p.status != PAIR_NO_TARGET; };
+            if (is_err(costs[k])) continue;                                       // a refusal of either search: the pair's answer is not proven
+            if (is_err(other[k])) { costs[k] = std::move(other[k]); continue; }
+            const bool a_ok = costs[k].status == PAIR_OK, b_ok = other[k].status == PAIR_OK;
+            if (b_ok && (!a_ok || other[k].cost < costs[k].cost)) costs[k] = std::move(other[k]);
+        }
+    } else {
+        const int rc1 = run_engines(ao, costs);
+        if (rc1 != TSA_OK) return rc1;
     }
     auto t2 = std::chrono::steady_clock::now();
     for (size_t i = 0; i < n; i++) {

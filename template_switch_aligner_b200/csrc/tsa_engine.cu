@@ -638,7 +638,10 @@ void Engine::run_staged() {
     // usually already contain the optimum.  Running them alone first gives the full rounds a tight upper bound, so
     // that the expensive forward kinds are pruned with ub = best + 1 instead of the deepening threshold.
     unsigned full_mask = 0, rev_mask = 0;
-    for (int k = 0; k < dev_.n_kinds; k++) { full_mask |= 1u << k; if (dev_.kinds[k].d == 1) rev_mask |= 1u << k; }
+    for (int k = 0; k < dev_.n_kinds; k++) {
+        if (I.opt.primary_filter != 0 && dev_.kinds[k].p != I.opt.primary_filter - 1) continue;   // descendant strategy: one primary only
+        full_mask |= 1u << k; if (dev_.kinds[k].d == 1) rev_mask |= 1u << k;
+    }
     const bool scout = I.opt.scout_round && rev_mask != 0 && rev_mask != full_mask;
     const unsigned clear_gx = (unsigned)std::min<size_t>(512, std::max<size_t>(8, (I.cells / std::max<size_t>(1, I.npairs)) / 8192));   // blocks per pair
     for (int round = 0;; round++) {

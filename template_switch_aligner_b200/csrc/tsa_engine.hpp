@@ -19,6 +19,7 @@ struct AlignOptions {
     bool no_windows = false;       // developer knob: pairs of 545..1055 characters skip the column-window stage (parity tests)
     bool test_small_windows = false;  // emulator builds only: pairs wider than 48 use 96 / 160-column windows (CPU tests of the window logic)
     size_t chunk_bytes = 0;        // HBM budget of one resident chunk of pairs; 0 = half of the free device memory
+    int primary_filter = 0;        // 0: every kind; 1 / 2: only template switches whose primary (descendant) is the reference / the query
     bool memory_limit_strict = false;   // --memory-limit given: a pair that does not fit the budget on its own is reported (PAIR_MEMORY_LIMIT), not staged
 };
 

@@ -79,7 +79,10 @@ TSA_DEV int ffs_u32(uint32_t v) { return __ffs((int)v); }                       
 TSA_DEV int ld_acquire_s32(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 TSA_DEV void st_release_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 TSA_DEV int ld_cg_s32(const int* p) { return __ldcg(p); }
-TSA_DEV void spin_pause() { __nanosleep(40); }
+#ifndef TSA_SPIN_NS
+#define TSA_SPIN_NS 40
+#endif
+TSA_DEV void spin_pause() { __nanosleep(TSA_SPIN_NS); }
 }  // namespace tsa
 
 #else

@@ -4,8 +4,11 @@
 // util.rs:14-28 (config directory), the stdout block of alignment_result.rs:736-777 and the TOML layout of
 // alignment_result.rs:32-81 as written by align/template_switch_distance_type_selectors.rs:442-449.
 //
-// Not done by this build (accepted, reported on stderr): extend_beyond_range / equal-cost ranges post-processing
-// (alignment_result.rs:247-573); `show`, `preprocess` and the other alignment methods.
+// Post-processing (extension beyond the range, equal-cost ranges: alignment_result.rs:247-573) runs inside the library call.
+// Batch front-end (not in the reference, whose fasta_parser.rs:157-173 accepts exactly two records): `--pairs FILE` takes a
+// multi-FASTA with an even number of records (records 2k, 2k+1 = reference, query of pair k) or a TSV (name, reference, query),
+// aligns all pairs with ONE tsa_align_batch call and writes one TOML per pair (`-o DIR`) and / or a JSON-lines stream.
+// Not part of this build: `show`, `preprocess` and the other alignment methods.
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -124,7 +127,8 @@ std::string complement_text(const std::string& s, bool rna) {
 
 struct Cli {
     std::string pair_fasta, reference, query, output, config_dir = "sample_tsa_config", alphabet = "dna-n", skip, method = "a-star-template-switch";
-    std::string rq_ranges;
+    std::string rq_ranges, pairs_file, jsonl;
+    int total_length_strategy = 0, descendant_strategy = 0;
     bool no_ts = false, embedded = false, dont_extend = false;
     long long ref_off = -1, ref_lim = -1, qry_off = -1, qry_lim = -1;
     unsigned long long cost_limit = UINT64_MAX, memory_limit = UINT64_MAX;
@@ -136,7 +140,8 @@ void usage() {
             "Usage: tsalign-b200 align [-p PAIR_FASTA | -r REFERENCE -q QUERY] [-o OUTPUT] [-a ALPHABET] [--skip-characters S]\n"
             "       [-c CONFIGURATION_DIRECTORY] [--no-ts] [--cost-limit N] [--memory-limit BYTES] [--rq-ranges R<a>..<b>Q<c>..<d>]\n"
             "       [--reference-offset N] [--reference-limit N] [--query-offset N] [--query-limit N] [--use-embedded-rq-ranges]\n"
-            "       [--dont-extend-beyond-range] [--device N] (search-heuristic flags of tsalign are accepted and ignored)\n");
+            "       [--dont-extend-beyond-range] [--device N] (search-heuristic flags of tsalign are accepted and ignored)\n"
+            "   or: tsalign-b200 align --pairs MULTI_FASTA_OR_TSV [-o OUTPUT_DIRECTORY] [--output-jsonl FILE] [same options]   (batch: one GPU call)\n");
 }
 
 }  // namespace
@@ -149,7 +154,7 @@ int main(int argc, char** argv) {
     Cli cli;
     // flags with a value that only steer the reference's search heuristics (never the optimal cost): accepted, ignored
     const char* ignored_with_value[] = {"-l", "--log-level", "--cache-directory", "-k", "--ts-node-ord-strategy", "--ts-min-length-strategy", "--ts-chaining-strategy",
-                                        "--ts-total-length-strategy", "--max-chaining-successors", "--max-exact-cost-function-cost", "--chaining-closed-list", "--chaining-open-list"};
+                                        "--max-chaining-successors", "--max-exact-cost-function-cost", "--chaining-closed-list", "--chaining-open-list"};
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i], val;
         bool has_inline = false;
@@ -178,7 +183,10 @@ int main(int argc, char** argv) {
         else if (a == "--skip-characters") cli.skip = value();
         else if (a == "-c" || a == "--configuration-directory") cli.config_dir = value();
         else if (a == "--alignment-method") cli.method = value();
-        else if (a == "--ts-descendant-strategy") { if (value() != "allow-any") die("--ts-descendant-strategy allow-only-all-equal is not supported by tsalign-b200", 2); }
+        else if (a == "--ts-descendant-strategy") { const std::string v = value(); if (v == "allow-any") cli.descendant_strategy = 0; else if (v == "allow-only-all-equal") cli.descendant_strategy = 1; else die("invalid value '" + v + "' for '--ts-descendant-strategy'", 2); }
+        else if (a == "--ts-total-length-strategy") { const std::string v = value(); if (v == "maximise") cli.total_length_strategy = 0; else if (v == "none") cli.total_length_strategy = 1; else die("invalid value '" + v + "' for '--ts-total-length-strategy'", 2); }
+        else if (a == "--pairs") cli.pairs_file = value();
+        else if (a == "--output-jsonl") cli.jsonl = value();
         else if (a == "--no-ts") cli.no_ts = true;
         else if (a == "--force-no-preprocessing" || a == "--force-label-correcting") {}
         else if (a == "--cost-limit") cli.cost_limit = number();
@@ -199,26 +207,15 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 6; k++) if (cli.alphabet == ALPHABETS[k]) alphabet = k;
     if (alphabet < 0) die("invalid value '" + cli.alphabet + "' for '--alphabet'", 2);
 
-    // ---- input (align.rs:304-335) ----
-    Record ref, qry;
-    if (!cli.pair_fasta.empty()) {
-        if (!cli.reference.empty() || !cli.query.empty()) die("the argument '--pair-fasta' cannot be used with '--reference' / '--query'", 2);
-        std::vector<Record> recs = parse_fasta(cli.pair_fasta);
-        if (recs.size() != 2) die("Pair fasta file must contain exactly two records, but it contains " + std::to_string(recs.size()));
-        ref = recs[0]; qry = recs[1];
-    } else if (!cli.reference.empty() && !cli.query.empty()) {
-        std::vector<Record> a = parse_fasta(cli.reference), b = parse_fasta(cli.query);
-        if (a.size() != 1 || b.size() != 1) die("Single fasta files must contain exactly one record");
-        ref = a[0]; qry = b[0];
-    } else die("No fasta input file given");
     if (cli.embedded && cli.skip.find('|') != std::string::npos) die("Using embedded RQ ranges, but '|' is part of the skip characters");
+    // drop skip characters, upper-case (align.rs:304-335), then the ranges (align.rs:338-379, 516-599)
+    auto prepare = [&](Record& ref, Record& qry, long long& ro, long long& rl, long long& qo, long long& ql) {
     for (Record* r : {&ref, &qry}) {
         std::string s;
         for (char c : r->seq) if (cli.skip.find(c) == std::string::npos) s.push_back((char)toupper((unsigned char)c));
         r->seq = s;
     }
-    // ---- ranges (align.rs:338-379, 516-599) ----
-    long long ro = 0, rl = -1, qo = 0, ql = -1;
+    ro = 0; rl = -1; qo = 0; ql = -1;
     if (cli.embedded) {
         if (!cli.rq_ranges.empty() || cli.ref_off >= 0 || cli.ref_lim >= 0 || cli.qry_off >= 0 || cli.qry_lim >= 0) die("Redundant specification of RQ ranges");
         auto split = [&](Record& r, const char* what, long long& off, long long& lim) {
@@ -261,6 +258,7 @@ int main(int argc, char** argv) {
         qo = cli.qry_off >= 0 ? cli.qry_off : qq0; ql = cli.qry_lim >= 0 ? cli.qry_lim : qq1;
     }
 
+    };
     // ---- cost model (util.rs:14-28) ----
     std::string cfg_path = cli.config_dir + "/config.tsa";
     std::ifstream cin_(cfg_path);
@@ -277,35 +275,28 @@ int main(int argc, char** argv) {
     opt.no_ts = cli.no_ts; opt.device = cli.device; opt.cost_limit = cli.cost_limit; opt.memory_limit = cli.memory_limit;
     // a_star_aligner.rs:238-253: extension unless --dont-extend-beyond-range, equal-cost ranges always
     opt.postprocess = TSA_POST_EQUAL_COST_RANGES | (cli.dont_extend ? 0 : TSA_POST_EXTEND_BEYOND_RANGE);
-    tsa_pair pair;
-    pair.reference = ref.seq.data(); pair.reference_len = ref.seq.size();
-    pair.query = qry.seq.data(); pair.query_len = qry.seq.size();
-    pair.reference_offset = ro; pair.reference_limit = rl; pair.query_offset = qo; pair.query_limit = ql;
-    tsa_result res;
-    int rc = tsa_align_batch(cfg, &opt, &pair, 1, &res, err, sizeof(err));
-    if (rc != TSA_OK) die(std::string("alignment failed: ") + err);
-    if (res.status == TSA_ERR_INVALID_CHAR) die(std::string(strstr(res.message, "reference") ? "Reference" : "Query") + " contains non-alphabet character: " + res.message);
-    if (res.status != TSA_OK) die(std::string("alignment failed: ") + res.message);
-    if (res.status == TSA_OK && res.result_type == TSA_FOUND_TARGET) { ro = res.reference_offset; qo = res.query_offset; }   // statistics follow the extended range
-
-    // ---- statistics (alignment_result.rs:175-237) ----
-    const bool found = res.result_type == TSA_FOUND_TARGET;
-    const double cost = (double)res.cost;
-    const double per_base = (ref.seq.size() + qry.seq.size()) ? 2.0 * cost / (double)(ref.seq.size() + qry.seq.size()) : 0.0;
-    int ts_amount = 0;
-    for (size_t i = 0; i < res.n_ops; i++) ts_amount += res.ops[i].type == TSA_OP_TS_EXIT;
-    std::string result_line;
-    switch (res.result_type) {
-    case TSA_FOUND_TARGET: result_line = "Reached target with cost " + std::to_string(res.cost); break;
-    case TSA_EXCEEDED_COST_LIMIT: result_line = "Exceeded cost limit of " + std::to_string(res.cost); break;
-    case TSA_EXCEEDED_MEMORY_LIMIT: result_line = "Exceeded memory limit, but reached a maximum cost of " + std::to_string(res.cost); break;
-    default: result_line = "Found no target";
-    }
-    const std::string ref_name = ref.id + " " + ref.comment, qry_name = qry.id + " " + qry.comment;  // align.rs:418-419
-
-    if (!cli.output.empty()) {
-        std::ofstream out(cli.output);
-        if (!out) die("Unable to open output file \"" + cli.output + "\"");
+    opt.total_length_strategy = cli.total_length_strategy; opt.descendant_strategy = cli.descendant_strategy;
+    const bool rna = alphabet == TSA_ALPHABET_RNA || alphabet == TSA_ALPHABET_RNA_N || alphabet == TSA_ALPHABET_RNA_IUPAC;
+    auto result_line_of = [](const tsa_result& res) -> std::string {
+        switch (res.result_type) {
+        case TSA_FOUND_TARGET: return "Reached target with cost " + std::to_string(res.cost);
+        case TSA_EXCEEDED_COST_LIMIT: return "Exceeded cost limit of " + std::to_string(res.cost);
+        case TSA_EXCEEDED_MEMORY_LIMIT: return "Exceeded memory limit, but reached a maximum cost of " + std::to_string(res.cost);
+        default: return "Found no target";
+        }
+    };
+    auto per_base_of = [](const tsa_result& res, const Record& ref, const Record& qry) {
+        return (ref.seq.size() + qry.seq.size()) ? 2.0 * (double)res.cost / (double)(ref.seq.size() + qry.seq.size()) : 0.0;
+    };
+    // TOML result file (alignment_result.rs:32-81 as written by align/template_switch_distance_type_selectors.rs:442-449)
+    auto write_toml = [&](const std::string& path, const tsa_result& res, const Record& ref, const Record& qry, long long ro, long long qo) {
+        const bool found = res.result_type == TSA_FOUND_TARGET;
+        const double cost = (double)res.cost, per_base = per_base_of(res, ref, qry);
+        int ts_amount = 0;
+        for (size_t i = 0; i < res.n_ops; i++) ts_amount += res.ops[i].type == TSA_OP_TS_EXIT;
+        const std::string ref_name = ref.id + " " + ref.comment, qry_name = qry.id + " " + qry.comment;  // align.rs:418-419
+        std::ofstream out(path);
+        if (!out) die("Unable to open output file \"" + path + "\"");
         out << "type = " << (found ? "\"WithTarget\"" : "\"WithoutTarget\"") << "\n";
         if (found) {
             out << "alignment = [";
@@ -333,11 +324,114 @@ int main(int argc, char** argv) {
         case TSA_EXCEEDED_MEMORY_LIMIT: out << "astar_result_type = \"ExceededMemoryLimit\"\nmax_cost = " << res.cost << "\n"; break;
         default: out << "astar_result_type = \"NoTarget\"\n";
         }
-        const bool rna = alphabet == TSA_ALPHABET_RNA || alphabet == TSA_ALPHABET_RNA_N || alphabet == TSA_ALPHABET_RNA_IUPAC;
         out << "\n[sequences]\nreference_name = " << toml_string(ref_name) << "\nreference = " << toml_string(ref.seq) << "\nreference_rc = "
             << toml_string(complement_text(ref.seq, rna)) << "\nquery_name = " << toml_string(qry_name) << "\nquery = " << toml_string(qry.seq) << "\nquery_rc = "
             << toml_string(complement_text(qry.seq, rna)) << "\n";
+    };
+
+    // ---- batch front-end: --pairs ------------------------------------------------------------------------------------------
+    if (!cli.pairs_file.empty()) {
+        if (!cli.pair_fasta.empty() || !cli.reference.empty() || !cli.query.empty()) die("the argument '--pairs' cannot be used with '--pair-fasta' / '--reference' / '--query'", 2);
+        std::vector<Record> refs, qrys;
+        {
+            std::ifstream probe(cli.pairs_file, std::ios::binary);
+            if (!probe) die("Unable to open input file \"" + cli.pairs_file + "\"");
+            int c = probe.peek();
+            while (c == '\n' || c == '\r' || c == ' ') { probe.get(); c = probe.peek(); }
+            if (c == '>') {
+                std::vector<Record> recs = parse_fasta(cli.pairs_file);
+                if (recs.size() % 2) die("Pair list fasta file must contain an even number of records, but it contains " + std::to_string(recs.size()));
+                for (size_t k = 0; k + 1 < recs.size(); k += 2) { refs.push_back(recs[k]); qrys.push_back(recs[k + 1]); }
+            } else {
+                // TSV: name <TAB> reference <TAB> query (a two-column line has no name)
+                std::string line;
+                size_t ln = 0;
+                while (std::getline(probe, line)) {
+                    ln++;
+                    if (!line.empty() && line.back() == '\r') line.pop_back();
+                    if (line.empty() || line[0] == '#') continue;
+                    std::vector<std::string> f;
+                    size_t a = 0;
+                    for (;;) { size_t b = line.find('\t', a); f.push_back(line.substr(a, b == std::string::npos ? b : b - a)); if (b == std::string::npos) break; a = b + 1; }
+                    if (f.size() != 2 && f.size() != 3) die("line " + std::to_string(ln) + " of \"" + cli.pairs_file + "\": expected name<TAB>reference<TAB>query");
+                    Record r, q;
+                    r.id = f.size() == 3 ? f[0] : "pair" + std::to_string(refs.size()); q.id = r.id;
+                    r.comment = "reference"; q.comment = "query";
+                    r.seq = f[f.size() - 2]; q.seq = f[f.size() - 1];
+                    refs.push_back(r); qrys.push_back(q);
+                }
+            }
+        }
+        const size_t n = refs.size();
+        std::vector<tsa_pair> pairs(n);
+        for (size_t k = 0; k < n; k++) {
+            long long ro, rl, qo, ql;
+            prepare(refs[k], qrys[k], ro, rl, qo, ql);
+            pairs[k].reference = refs[k].seq.data(); pairs[k].reference_len = refs[k].seq.size();
+            pairs[k].query = qrys[k].seq.data(); pairs[k].query_len = qrys[k].seq.size();
+            pairs[k].reference_offset = ro; pairs[k].reference_limit = rl; pairs[k].query_offset = qo; pairs[k].query_limit = ql;
+        }
+        std::vector<tsa_result> results(n ? n : 1);
+        int rc = tsa_align_batch(cfg, &opt, pairs.data(), n, results.data(), err, sizeof(err));
+        if (rc != TSA_OK) die(std::string("alignment failed: ") + err);
+        std::ofstream jl;
+        if (!cli.jsonl.empty()) { jl.open(cli.jsonl); if (!jl) die("Unable to open output file \"" + cli.jsonl + "\""); }
+        auto json_string = [](const std::string& s) { std::string o = "\""; for (char c : s) { if (c == '"' || c == '\\') { o.push_back('\\'); o.push_back(c); } else if ((unsigned char)c < 0x20) o += ' '; else o.push_back(c); } return o + "\""; };
+        size_t failed = 0;
+        // stdout: one line per pair: index, reference id, query id, result, cost, template switches, CIGAR
+        for (size_t k = 0; k < n; k++) {
+            const tsa_result& res = results[k];
+            if (res.status != TSA_OK) {
+                failed++;
+                printf("%zu\t%s\t%s\tError\t-\t-\t%s\n", k, refs[k].id.c_str(), qrys[k].id.c_str(), res.message);
+                if (jl.is_open()) jl << "{\"index\": " << k << ", \"reference_name\": " << json_string(refs[k].id) << ", \"query_name\": " << json_string(qrys[k].id) << ", \"error\": " << json_string(res.message) << "}\n";
+                continue;
+            }
+            static const char* const KINDS[] = {"FoundTarget", "ExceededCostLimit", "ExceededMemoryLimit", "NoTarget"};
+            const bool found = res.result_type == TSA_FOUND_TARGET;
+            const std::string cg = found ? cigar(res) : std::string("-");
+            printf("%zu\t%s\t%s\t%s\t%llu\t%d\t%s\n", k, refs[k].id.c_str(), qrys[k].id.c_str(), KINDS[res.result_type], (unsigned long long)res.cost, res.template_switches, cg.c_str());
+            const long long ro = found ? res.reference_offset : pairs[k].reference_offset, qo = found ? res.query_offset : pairs[k].query_offset;
+            if (jl.is_open())
+                jl << "{\"index\": " << k << ", \"reference_name\": " << json_string(refs[k].id) << ", \"query_name\": " << json_string(qrys[k].id) << ", \"result\": \"" << KINDS[res.result_type]
+                   << "\", \"cost\": " << res.cost << ", \"template_switches\": " << res.template_switches << ", \"reference_offset\": " << ro << ", \"query_offset\": " << qo
+                   << ", \"reference_limit\": " << res.reference_limit << ", \"query_limit\": " << res.query_limit << ", \"cigar\": " << json_string(cg) << "}\n";
+            if (!cli.output.empty()) write_toml(cli.output + "/" + std::to_string(k) + ".toml", res, refs[k], qrys[k], ro, qo);
+        }
+        fprintf(stderr, "%zu pairs aligned in one batch call (%zu with a per-pair error), %.3f s\n", n, failed, n ? results[0].duration_seconds * (double)n : 0.0);
+        tsa_results_free(results.data(), n);
+        tsa_config_free(cfg);
+        return failed ? 1 : 0;
     }
+
+    // ---- single pair (align.rs:304-335) ------------------------------------------------------------------------------------
+    Record ref, qry;
+    if (!cli.pair_fasta.empty()) {
+        if (!cli.reference.empty() || !cli.query.empty()) die("the argument '--pair-fasta' cannot be used with '--reference' / '--query'", 2);
+        std::vector<Record> recs = parse_fasta(cli.pair_fasta);
+        if (recs.size() != 2) die("Pair fasta file must contain exactly two records, but it contains " + std::to_string(recs.size()));
+        ref = recs[0]; qry = recs[1];
+    } else if (!cli.reference.empty() && !cli.query.empty()) {
+        std::vector<Record> a = parse_fasta(cli.reference), b = parse_fasta(cli.query);
+        if (a.size() != 1 || b.size() != 1) die("Single fasta files must contain exactly one record");
+        ref = a[0]; qry = b[0];
+    } else die("No fasta input file given");
+    long long ro, rl, qo, ql;
+    prepare(ref, qry, ro, rl, qo, ql);
+    tsa_pair pair;
+    pair.reference = ref.seq.data(); pair.reference_len = ref.seq.size();
+    pair.query = qry.seq.data(); pair.query_len = qry.seq.size();
+    pair.reference_offset = ro; pair.reference_limit = rl; pair.query_offset = qo; pair.query_limit = ql;
+    tsa_result res;
+    int rc = tsa_align_batch(cfg, &opt, &pair, 1, &res, err, sizeof(err));
+    if (rc != TSA_OK) die(std::string("alignment failed: ") + err);
+    if (res.status == TSA_ERR_INVALID_CHAR) die(std::string(strstr(res.message, "reference") ? "Reference" : "Query") + " contains non-alphabet character: " + res.message);
+    if (res.status != TSA_OK) die(std::string("alignment failed: ") + res.message);
+    if (res.status == TSA_OK && res.result_type == TSA_FOUND_TARGET) { ro = res.reference_offset; qo = res.query_offset; }   // statistics follow the extended range
+    const bool found = res.result_type == TSA_FOUND_TARGET;
+    const double per_base = per_base_of(res, ref, qry);
+    const std::string result_line = result_line_of(res);
+    if (!cli.output.empty()) write_toml(cli.output, res, ref, qry, ro, qo);
 
     if (found) printf("CIGAR: %s\n", cigar(res).c_str()); else printf("No alignment found\n");
     printf("%s\nReference offset: %lld\nQuery offset: %lld\nCost per base: %.2f\nOpened nodes: 0\nClosed nodes: 0\nSuboptimal openend nodes: 0\n"

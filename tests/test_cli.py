@@ -98,3 +98,35 @@ def test_errors(workdir):
     assert r.returncode == 1 and "Redundant" in r.stderr
     r = run(workdir, "align", "-p", "test_files/twin_a.fa", "-c", "nowhere")
     assert r.returncode == 1 and "config" in r.stderr
+
+
+def test_batch_front_end(workdir, pairs):
+    # --pairs: a multi-FASTA of several pairs (records 2k, 2k+1) and a TSV go through ONE tsa_align_batch call; every pair gets the
+    # result the single-pair CLI gives it (the reference's own front-end accepts exactly two records, fasta_parser.rs:157-173)
+    import json
+    names = ("twin_a.fa", "twin_show_ts_indel1.fa", "twin_10_ts.fa")
+    (workdir / "batch.fa").write_text("".join(pairs[n]["raw"] if pairs[n]["raw"].endswith("\n") else pairs[n]["raw"] + "\n" for n in names))
+    os.makedirs(workdir / "out_dir", exist_ok=True)
+    r = run(workdir, "align", "--pairs", "batch.fa", "-o", "out_dir", "--output-jsonl", "out.jsonl")
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split("\t") for ln in r.stdout.splitlines()]
+    assert len(rows) == len(names) and [row[0] for row in rows] == ["0", "1", "2"]
+    recs = [json.loads(ln) for ln in (workdir / "out.jsonl").read_text().splitlines()]
+    for k, name in enumerate(names):
+        single = run(workdir, "align", "-p", f"test_files/{name}", "-o", f"single_{k}.toml")
+        assert single.returncode == 0, single.stderr
+        cigar = single.stdout.splitlines()[0].split(": ", 1)[1]
+        assert rows[k][3] == "FoundTarget" and rows[k][6] == cigar and recs[k]["cigar"] == cigar
+        a, b = tomllib.loads((workdir / "out_dir" / f"{k}.toml").read_text()), tomllib.loads((workdir / f"single_{k}.toml").read_text())
+        for key in ("duration_seconds",):
+            a.pop(key); b.pop(key)
+        assert a == b and recs[k]["cost"] == a["result"]["cost"]
+    # TSV input, --no-ts, a pair with a character outside the alphabet is reported and the rest of the batch still answered
+    (workdir / "batch.tsv").write_text("p0\tACGTACGTAC\tACGTTCGTAC\n# comment\nACGT\tACG\np2\tACGZ\tACGT\n")
+    r = run(workdir, "align", "--pairs", "batch.tsv", "--no-ts")
+    rows = [ln.split("\t") for ln in r.stdout.splitlines()]
+    assert r.returncode == 1 and len(rows) == 3
+    assert rows[0][1] == "p0" and rows[0][3:6] == ["FoundTarget", "2", "0"] and rows[0][6] == "4=1X5="
+    assert rows[1][1] == "pair1" and rows[1][3] == "FoundTarget" and rows[2][3] == "Error"
+    odd = run(workdir, "align", "--pairs", "test_files/reference_a.fa")
+    assert odd.returncode != 0 and "even number of records" in odd.stderr

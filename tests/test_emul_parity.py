@@ -170,3 +170,35 @@ def test_layer_cap_mixed_batch_emulated(configs):
                 assert all(g.status == 0 for g in res)
             assert res[5].status == 0 and res[5].cost == 0
     assert (1, 9) in seen and (1, 0) in seen
+
+
+def test_descendant_strategy_emulated(configs, pairs):
+    # --ts-descendant-strategy allow-only-all-equal (strategies/descendant.rs:22-104): all template switches of an alignment share
+    # their primary.  Expected = the better of the oracle's optima under the cost model with only reference-primary kinds and with
+    # only query-primary kinds (base cost of the other kinds = inf).
+    import re
+    text = configs["sample"]
+
+    def only(primary):
+        other = "q" if primary == "r" else "r"
+        return re.sub(rf"^({other}[rq][fr]_cost\s*=\s*)\S+", r"\1inf", text, flags=re.M)
+
+    ocfg = parse_config_any(text)
+    flats = [oracle.FlatConfig(parse_config_any(only(p))) for p in "rq"]
+    items = parity.test_file_pairs(pairs, ocfg.alphabet, 40)[:12]
+    items += [("two", "ACGTTGCATGCAAGTCCGATAGGCTTACGATC", "ACGTTGCAACTTGCATCCGATAGAAGCCTATC")]
+    aligner = tsa.Aligner(costs=text, alphabet=ocfg.alphabet, lib=emul(), descendant_strategy="allow-only-all-equal")
+    free = tsa.Aligner(costs=text, alphabet=ocfg.alphabet, lib=emul())
+    got = aligner.align_batch([(r, q) for _, r, q in items])
+    unconstrained = free.align_batch([(r, q) for _, r, q in items])
+    differs = 0
+    for (name, r, q), g, u in zip(items, got, unconstrained):
+        want = min(oracle.dp_align(f, r, q).cost for f in flats)
+        assert g.status == 0 and g.found and g.cost == want, (name, g.cost, want)
+        assert g.cost >= u.cost
+        differs += g.cost != u.cost
+        primaries = {op[2] for op in g.ops if op[1] == oracle.OP_TS_ENTRANCE}
+        assert len(primaries) <= 1, (name, g.ops)
+        flat = oracle.FlatConfig(ocfg)
+        cost, er, eq, ok = oracle.rescore(flat, r, q, [oracle.Op(*o) for o in g.ops], g.range[0], g.range[2])
+        assert ok and cost == g.cost

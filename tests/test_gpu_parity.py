@@ -363,3 +363,34 @@ def test_no_ts_random_models_long_gpu(lib):
         parity.check_batch(aligner, flat, cases, no_ts=True, label=f"wave seed {seed}")
         checked += len(cases)
     assert checked == 48
+
+
+def test_cli_binary_batch_gpu(lib, tmp_path):
+    # the real `tsalign-b200` binary (linked against libtsalign_b200.so) on a B200: batch front-end and single-pair mode against
+    # the committed A* costs of the read-pair sample and the library's own answers
+    import json
+    import os
+    import subprocess
+    from conftest import load_golden
+    cli = os.path.join(os.path.dirname(os.path.abspath(_lib.LIB_PATH)), "tsalign-b200")
+    assert os.path.exists(cli), "template_switch_aligner_b200/tsalign-b200 is not built (python -c 'import __graft_entry__ as g; g.build()')"
+    os.makedirs(tmp_path / "cfg")
+    (tmp_path / "cfg" / "config.tsa").write_text(workloads.sample_config_text())
+    gold = {p["index"]: p for p in load_golden("astar_c2.json")["pairs"] if p["result"] == "FoundTarget"}
+    ids = sorted(gold)
+    with open(tmp_path / "reads.fa", "w") as fh:
+        for i in ids:
+            r, q = workloads.read_pair(i, 150)
+            fh.write(f">r{i} reference\n{r}\n>q{i} query\n{q}\n")
+    out = subprocess.run([cli, "align", "--pairs", "reads.fa", "-c", "cfg", "--output-jsonl", "reads.jsonl"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    recs = [json.loads(ln) for ln in open(tmp_path / "reads.jsonl")]
+    assert [r["cost"] for r in recs] == [gold[i]["cost"] for i in ids] and all(r["result"] == "FoundTarget" for r in recs)
+    want = tsa.Aligner(costs=workloads.sample_config_text(), device=0, postprocess=api.POST_EXTEND_BEYOND_RANGE | api.POST_EQUAL_COST_RANGES).align_batch([workloads.read_pair(i, 150) for i in ids])
+    assert [r["template_switches"] for r in recs] == [w.template_switches for w in want]
+    # single-pair mode, TOML file
+    r, q = workloads.read_pair(ids[0], 150)
+    (tmp_path / "one.fa").write_text(f">ref\n{r}\n>qry\n{q}\n")
+    one = subprocess.run([cli, "align", "-p", "one.fa", "-c", "cfg", "-o", "one.toml"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0 and f"Reached target with cost {gold[ids[0]]['cost']}" in one.stdout, one.stderr
+    assert "astar_result_type = \"FoundTarget\"" in (tmp_path / "one.toml").read_text()
