@@ -34,7 +34,7 @@ struct BandArgs {
     int group;               // strips per column group
     int row0, row1;          // rows row0 + 1 .. row1 are computed from the state of row row0 (row0 == 0: row 0 too, from the root)
     int ck_col0;             // first column of the band: checkpoint entry of column j = j - ck_col0 + 1 (entry 0: the column left of the band)
-    const int* ckpt_in;      // row0 > 0: [entry][3] states N, Dl, I of row row0
+    const int* ckpt_in;      // row0 > 0: [entry][3] of row row0: cheapest state M, deletion state Dl, min(N, I) (what the row below reads)
     int* ckpt_out;           // forward pass: [row / interval - 1][entry][3]; null: no checkpoints are stored
     int interval;            // checkpoint every `interval` rows
     long long ckpt_stride;   // ints per checkpoint row
@@ -55,15 +55,9 @@ struct BandArgs {
 struct WalkState { int i, j, g, need; long long cost; int status; int pad; };   // status: 0 walking, 1 reached the root, < 0 error
 enum { WALK_GOING = 0, WALK_DONE = 1, WALK_ERR = -1, WALK_OPS_FULL = -2 };
 
-template <bool TRACE>
-TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_affine_band(const DevConfig* cfg, BandArgs ba) {
-    TSA_SHARED_DECL(smem_raw);
-    constexpr int CB = WAVE_CB;
-    const int lane = lane_id();
+// Shared memory tables of the wavefront kernels: substitution costs [r][q] with row stride A + 1, then the gap costs by character.
+TSA_DEV void band_stage_tables(const DevConfig* cfg, int* subP, int* openP, int* extP) {
     const int A = cfg->A, ws = A + 1;
-    int* subP = reinterpret_cast<int*>(smem_raw);
-    int* openP = subP + MAX_ALPHABET * MAX_ALPHABET;
-    int* extP = openP + MAX_ALPHABET;
     for (int t = (int)threadIdx.x; t < A * ws; t += (int)blockDim.x) {
         const int r = t / ws, q = t % ws;
         subP[t] = q < A ? imin(cfg->sub[0][r * MAX_ALPHABET + q], INF32) : INF32;
@@ -73,17 +67,19 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
         extP[t] = t < A ? imin(cfg->ext[0][t], INF32) : INF32;
     }
     sync_block();
+}
+
+// One strip (global strip index s) of the launch described by `ba`, by one warp.
+template <bool TRACE>
+TSA_DEV void band_strip(const BandArgs& ba, int s, int A, const int* subP, const int* openP, const int* extP) {
+    constexpr int CB = WAVE_CB;
+    const int lane = lane_id();
+    const int ws = A + 1;
     const int nn = ba.nn, mm = ba.mm, row0 = ba.row0, row1 = ba.row1;
     const uint8_t* R = ba.R;
     const uint8_t* Q = ba.Q;
     const long long col_rows = (long long)nn + 1;
-
-    for (;;) {
-        int tk = 0;
-        if (lane == 0) tk = atomic_add_s32(ba.ticket, 1);
-        tk = (int)shfl_idx((uint32_t)tk, 0);
-        if (tk >= ba.n_strips) break;
-        const int s = ba.s_lo + tk;
+    {
         const bool last_strip = s == ba.s_total - 1;
         const int j0 = s * WAVE_SW + lane * CB;
         // where the boundary column comes from and where this strip's last column goes
@@ -140,6 +136,12 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
         const bool is_root_lane = s == 0 && lane == 0;
         const int tcol = mm - j0;
         const int steps = (row1 - row0) + 32;
+        int* const ck_out = ba.ckpt_out;
+        const int ck_interval = imax(ba.interval, 1);
+        const long long dstride = ba.dstride;
+        const int row_base = ba.row_base;
+        const bool local_out = bnd_wr != nullptr && bnd_wr == ba.bnd_local;
+        int ck_phase = row0 % ck_interval;
         for (int st = 0; st < steps; st++) {
             if ((st & 31) == 0) { accept_chunk(st); request_chunk(st + 32); }
             int rch = (int)shfl_up((uint32_t)out_r, 1);
@@ -151,32 +153,28 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
             if (lane == 0) { rch = r0; lnd = n0; li = i0; }
             const int i = row0 + st - lane;
             if (i < row0 || i > row1) continue;
+            // phase of row i within the checkpoint interval, kept incrementally (a lane visits the rows row0, row0 + 1, ... in order)
+            const int ph = ck_phase;
+            ck_phase = ck_phase + 1 == ck_interval ? 0 : ck_phase + 1;
             if (i == row0 && row0 > 0) {
-                // the checkpoint row: its states are loaded instead of computed
-                int left_nd = INF32, left_i = INF32;
+                // the checkpoint row: what the next row needs of it is loaded instead of computed: per column the cheapest state M,
+                // the deletion state Dl and min(N, I) -- exactly the registers the row below reads -- and M of the column to the left
+                // (the diagonal predecessor of row0 + 1, column j0; entry 0 = the column left of the band)
 #pragma unroll
                 for (int c = 0; c < CB; c++) {
                     const int j = j0 + c;
-                    int vn = INF32, vd = INF32, vi = INF32;
+                    int vm = INF32, vd = INF32, vni = INF32;
                     if (j <= mm) {
                         const int* e = ba.ckpt_in + (long long)(j - ba.ck_col0 + 1) * 3;
-                        vn = e[0]; vd = e[1]; vi = e[2];
+                        vm = e[0]; vd = e[1]; vni = e[2];
                     }
-                    Mup[c] = imin(vn, imin(vd, vi)); Dlup[c] = vd; NIup[c] = imin(vn, vi);
-                    left_nd = imin(vn, vd); left_i = vi;
+                    Mup[c] = vm; Dlup[c] = vd; NIup[c] = vni;
                 }
-                // M of the column to the left (the diagonal predecessor of row0 + 1, column j0): the neighbour lane's last column, or
-                // for lane 0 the checkpoint entry of column j0 - 1 (entry 0 = the column left of the band, stored by the forward pass)
-                int dleft = imin(lnd, li);
-                if (lane == 0) {
-                    dleft = INF32;
-                    if (j0 >= 1) { const int* e = ba.ckpt_in + (long long)(j0 - 1 - ba.ck_col0 + 1) * 3; dleft = imin(e[0], imin(e[1], e[2])); }
-                }
-                diag_in = dleft;
-                out_nd = left_nd; out_i = left_i; out_r = rch;
-                // the next strip of the group validates the entry of this row like any other
-                if (lane == 31 && bnd_wr != nullptr && bnd_wr == ba.bnd_local)
-                    wave_bnd_store(bnd_wr + i, WaveBnd{(uint32_t)imin(left_nd, WAVE_SAT) | ((tag_out & 63u) << 26), (uint32_t)imin(left_i, WAVE_SAT) | ((tag_out >> 6) << 26)});
+                diag_in = j0 >= 1 && j0 - 1 <= mm ? ba.ckpt_in[(long long)(j0 - 1 - ba.ck_col0 + 1) * 3] : INF32;
+                // (the neighbour lane and the next strip read nothing of this row but the tag of its boundary entry)
+                out_nd = INF32; out_i = INF32; out_r = rch;
+                if (lane == 31 && local_out)
+                    wave_bnd_store(bnd_wr + i, WaveBnd{(uint32_t)WAVE_SAT | ((tag_out & 63u) << 26), (uint32_t)WAVE_SAT | ((tag_out >> 6) << 26)});
                 continue;
             }
             const int opR = i > 0 ? openP[rch] : INF32;
@@ -185,9 +183,7 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
             int prevM = i > 0 ? diag_in : INF32;
             int left_nd = lnd, left_i = li;
             uint32_t w0 = 0, w1 = 0;
-            const bool store_ck = !TRACE && ba.ckpt_out != nullptr && i > 0 && (i % ba.interval) == 0;
-            int* ck_row = store_ck ? ba.ckpt_out + (long long)(i / ba.interval - 1) * ba.ckpt_stride : nullptr;
-            if (store_ck && lane == 0 && j0 == ba.ck_col0) { ck_row[0] = lnd; ck_row[1] = INF32; ck_row[2] = li; }   // the column left of the band
+            const bool store_ck = !TRACE && ck_out != nullptr && i > 0 && ph == 0;
 #pragma unroll
             for (int c = 0; c < CB; c++) {
                 int nn_ = addmin_s32(prevM, srow[qoff[c]], INF32);
@@ -208,16 +204,22 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
                     if (dl < nn_) cd |= DIR_ND_IS_DL;
                     if (c < 4) w0 |= cd << (8 * c); else w1 |= cd << (8 * (c - 4));
                 }
-                if (store_ck && j0 + c <= mm) {
-                    int* e = ck_row + (long long)(j0 + c - ba.ck_col0 + 1) * 3;
-                    e[0] = nn_; e[1] = dl; e[2] = iv;
-                }
                 Mup[c] = M; Dlup[c] = dl; NIup[c] = imin(nn_, iv);
                 left_nd = nd; left_i = iv;
             }
+            if (store_ck) {
+                // checkpoint row: M, Dl, min(N, I) of every column, from the registers the next row reads
+                int* ck_row = ck_out + (long long)(i / ck_interval - 1) * ba.ckpt_stride;
+                if (lane == 0 && j0 == ba.ck_col0) { ck_row[0] = imin(lnd, li); ck_row[1] = INF32; ck_row[2] = INF32; }   // the column left of the band
+#pragma unroll
+                for (int c = 0; c < CB; c++) if (j0 + c <= mm) {
+                    int* e = ck_row + (long long)(j0 + c - ba.ck_col0 + 1) * 3;
+                    e[0] = Mup[c]; e[1] = Dlup[c]; e[2] = NIup[c];
+                }
+            }
             diag_in = imin(lnd, li);
             out_nd = left_nd; out_i = left_i; out_r = rch;
-            if (TRACE && j0 <= mm) *reinterpret_cast<WaveCodes8*>(dirp + (long long)(i - ba.row_base) * ba.dstride) = WaveCodes8{w0, w1};
+            if (TRACE && j0 <= mm) *reinterpret_cast<WaveCodes8*>(dirp + (long long)(i - row_base) * dstride) = WaveCodes8{w0, w1};
             if (lane == 31 && bnd_wr != nullptr) {
                 if ((left_nd >= WAVE_SAT && left_nd < INF32) || (left_i >= WAVE_SAT && left_i < INF32)) saturated = true;
                 wave_bnd_store(bnd_wr + i, WaveBnd{(uint32_t)imin(left_nd, WAVE_SAT) | ((tag_out & 63u) << 26), (uint32_t)imin(left_i, WAVE_SAT) | ((tag_out >> 6) << 26)});
@@ -230,6 +232,23 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
             tgt = reduce_min_s32(tgt);
             if (lane == 0) ba.result[0] = tgt;
         }
+    }
+}
+
+template <bool TRACE>
+TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_affine_band(const DevConfig* cfg, BandArgs ba) {
+    TSA_SHARED_DECL(smem_raw);
+    int* subP = reinterpret_cast<int*>(smem_raw);
+    int* openP = subP + MAX_ALPHABET * MAX_ALPHABET;
+    int* extP = openP + MAX_ALPHABET;
+    band_stage_tables(cfg, subP, openP, extP);
+    const int lane = lane_id();
+    for (;;) {
+        int tk = 0;
+        if (lane == 0) tk = atomic_add_s32(ba.ticket, 1);
+        tk = (int)shfl_idx((uint32_t)tk, 0);
+        if (tk >= ba.n_strips) break;
+        band_strip<TRACE>(ba, ba.s_lo + tk, cfg->A, subP, openP, extP);
     }
 }
 
@@ -248,10 +267,9 @@ struct WalkArgs {
     WalkState* state;        // in / out
 };
 
-TSA_KERNEL void k_band_walk(const DevConfig* cfg, WalkArgs wa) {
-    if (threadIdx.x >= 32 || blockIdx.x != 0) return;
+// The walk itself: all 32 lanes of one warp call it; returns the number of unit ops appended (wa.ops[0 .. pos)).
+TSA_DEV int band_walk(const DevConfig* cfg, const WalkArgs& wa, WalkState& st) {
     const int lane = lane_id();
-    WalkState st = *wa.state;
     int i = st.i, j = st.j, g = st.g, need = st.need, pos = 0;
     long long cost = st.cost;
     int status = WALK_GOING;
@@ -302,10 +320,117 @@ TSA_KERNEL void k_band_walk(const DevConfig* cfg, WalkArgs wa) {
             else { cost -= cfg->open[0][q]; need = 3; }
         }
     }
-    if (lane == 0) {
-        st.i = i; st.j = j; st.g = g; st.need = need; st.cost = cost; st.status = status;
-        *wa.state = st;
-        *wa.ops_len = pos;
+    st.i = i; st.j = j; st.g = g; st.need = need; st.cost = cost; st.status = status;
+    return pos;
+}
+
+static TSA_KERNEL void k_band_walk(const DevConfig* cfg, WalkArgs wa) {
+    if (threadIdx.x >= 32 || blockIdx.x != 0) return;
+    WalkState st = *wa.state;
+    const int pos = band_walk(cfg, wa, st);
+    if (lane_id() == 0) { *wa.state = st; *wa.ops_len = pos; }
+}
+
+// ---------------------------------------------------------------------------------------------------- batches of long pairs
+// BASELINE config 4 (many 10 kb pairs, --no-ts) WITH alignments and without a code matrix: the forward pass of every pair stores
+// checkpoint rows and group boundary columns exactly as one band of a long pair does (one BandArgs per pair, strips of all pairs
+// handed out through one ticket in (pair, strip) order), then one warp per pair recomputes, with codes, only the tiles its
+// optimal path crosses -- strip after strip into a per-warp scratch tile -- and walks them.  1 B/cell of codes (and the 14
+// instructions per cell that produce them in the forward pass) become ~6 % recomputed cells and 0.06 B/cell of checkpoints.
+constexpr int BB_INTERVAL = 256;   // checkpoint every 256 rows, tiles of 2 strips: a 10 kb pair recomputes ~6 % of its cells
+constexpr int BB_GROUP = 2;
+
+struct BandBatch {
+    const BandArgs* args;    // [n_pairs] forward description of every pair (s_lo = 0, all strips, row0 = 0, row1 = nn)
+    const int* pair_of;      // [n_pairs] staged pair index (Chunk arrays, TraceOut)
+    const int* prefix;       // [n_pairs + 1] first ticket of every pair
+    int n_pairs;
+    int* ticket;
+};
+
+static TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_band_batch_forward(const DevConfig* cfg, BandBatch bb) {
+    TSA_SHARED_DECL(smem_raw);
+    int* subP = reinterpret_cast<int*>(smem_raw);
+    int* openP = subP + MAX_ALPHABET * MAX_ALPHABET;
+    int* extP = openP + MAX_ALPHABET;
+    band_stage_tables(cfg, subP, openP, extP);
+    const int lane = lane_id();
+    const int total = bb.prefix[bb.n_pairs];
+    for (;;) {
+        int tk = 0;
+        if (lane == 0) tk = atomic_add_s32(bb.ticket, 1);
+        tk = (int)shfl_idx((uint32_t)tk, 0);
+        if (tk >= total) break;
+        int lo = 0, hi = bb.n_pairs - 1;                           // last pair whose first ticket is <= tk
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (bb.prefix[mid] <= tk) lo = mid; else hi = mid - 1; }
+        band_strip<false>(bb.args[lo], tk - bb.prefix[lo], cfg->A, subP, openP, extP);      // (the description stays in global memory: its fields are read once per strip)
+    }
+}
+
+// results of the forward pass into the per-pair arrays the rest of the engine reads
+static TSA_KERNEL void k_band_batch_finish(Chunk ck, BandBatch bb) {
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= bb.n_pairs) return;
+    const int b = bb.pair_of[k];
+    ck.best[b] = bb.args[k].result[0]; ck.best_layer[b] = 0; ck.active[b] = 0;
+    ck.next_active[b] = bb.args[k].result[1];      // boundary values saturated (WAVE_SAT)
+}
+
+struct BandBatchTrace {
+    uint8_t* tiles;          // per warp of the launch: codes of one tile, (interval + 1) rows of group * 256 bytes
+    long long tile_bytes;
+    WaveBnd* bnds;           // per warp: boundary between the strips of a tile, interval + 1 entries
+};
+
+static TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, 3) k_band_batch_trace(const DevConfig* cfg, Chunk ck, BandBatch bb, BandBatchTrace bt, TraceOut to) {
+    TSA_SHARED_DECL(smem_raw);
+    int* subP = reinterpret_cast<int*>(smem_raw);
+    int* openP = subP + MAX_ALPHABET * MAX_ALPHABET;
+    int* extP = openP + MAX_ALPHABET;
+    band_stage_tables(cfg, subP, openP, extP);
+    const int lane = lane_id();
+    const int wid = (int)blockIdx.x * WAVE_WARPS + (int)(threadIdx.x >> 5), nw = (int)gridDim.x * WAVE_WARPS;
+    uint8_t* tile = bt.tiles + (long long)wid * bt.tile_bytes;
+    for (int k = wid; k < bb.n_pairs; k += nw) {
+        const int b = bb.pair_of[k];
+        const BandArgs fa = bb.args[k];
+        const int best = ck.best[b];
+        if (best >= INF32) { if (lane == 0) { to.status[b] = TRACE_SKIPPED; to.ops_len[b] = 0; to.n_recs[b] = 0; } continue; }
+        const int IV = fa.interval, G = fa.group;
+        WalkState st;
+        st.i = fa.nn; st.j = fa.mm; st.g = 0; st.need = 1; st.cost = best; st.status = WALK_GOING; st.pad = 0;
+        uint8_t* ops = to.ops + to.ops_off[b];
+        const int cap = to.ops_cap[b];
+        int pos = 0;
+        while (st.status == WALK_GOING) {
+            if (st.j < 0) { st.status = WALK_ERR; break; }
+            const int kk = st.i == 0 ? 0 : (st.i - 1) / IV;
+            const int row0 = kk * IV, row1 = st.i;
+            const int s_hi = st.j / WAVE_SW, s_lo = (s_hi / G) * G;
+            BandArgs ta = fa;
+            ta.s_lo = s_lo; ta.n_strips = s_hi - s_lo + 1;
+            ta.row0 = row0; ta.row1 = row1;
+            ta.ckpt_in = kk > 0 ? fa.ckpt_out + (long long)(kk - 1) * fa.ckpt_stride : nullptr;
+            ta.ckpt_out = nullptr; ta.store_cols = 0;
+            ta.bnd_local = bt.bnds + (long long)wid * (IV + 1) - row0;      // indexed by the absolute row
+            ta.bnd_out = nullptr;
+            ta.dir = tile; ta.dstride = (long long)G * WAVE_SW; ta.row_base = kk > 0 ? row0 + 1 : 0;
+            for (int s = s_lo; s <= s_hi; s++) {
+                band_strip<true>(ta, s, cfg->A, subP, openP, extP);
+                sync_warp();      // the next strip reads this strip's boundary entries, the walk reads the codes
+            }
+            WalkArgs wa;
+            wa.R = fa.R; wa.Q = fa.Q; wa.dir = tile; wa.dstride = ta.dstride; wa.row_base = ta.row_base; wa.col_base = s_lo * WAVE_SW;
+            wa.row_lo = row0; wa.ops = ops + pos; wa.ops_cap = cap - pos; wa.ops_len = nullptr; wa.state = nullptr;
+            const WalkState before = st;
+            pos += band_walk(cfg, wa, st);
+            sync_warp();
+            if (st.status == WALK_GOING && st.i == before.i && st.j == before.j && st.need == before.need && st.g == before.g) st.status = WALK_ERR;
+        }
+        if (lane == 0) {
+            to.status[b] = st.status == WALK_DONE ? TRACE_OK : (st.status == WALK_OPS_FULL ? TRACE_ERR_OVERFLOW : TRACE_ERR_WALK);
+            to.ops_len[b] = pos; to.n_recs[b] = 0;
+        }
     }
 }
 

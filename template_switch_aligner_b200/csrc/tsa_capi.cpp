@@ -209,6 +209,8 @@ AlignOptions engine_options(const tsa_options& o) {
     a.scout_round = (o.reserved & 1) != 0;   // bit 0 of `reserved`: developer knob, enables the scouting round
     a.no_windows = (o.reserved & 2) != 0;    // bit 1: developer knob, medium pairs skip the column-window stage
     a.test_small_windows = (o.reserved & 4) != 0;   // bit 2: honoured by emulator builds only
+    if (o.reserved & 8) a.wave_checkpoints = 1;     // bit 3: developer knob, --no-ts alignments always through checkpoints (parity tests on short pairs)
+    if (o.reserved & 16) a.wave_checkpoints = -1;   // bit 4: developer knob, --no-ts alignments always through the code matrix
     if (a.traceback) a.max_layers = std::min(a.max_layers, (int)MAX_TRACE_LAYERS);
     if (o.memory_limit != UINT64_MAX) { a.chunk_bytes = (size_t)std::max<uint64_t>(o.memory_limit, (uint64_t)1 << 20); a.memory_limit_strict = true; }
     return a;

@@ -9,6 +9,7 @@
 #include <stdexcept>
 
 #include "tsa_kernels.cuh"
+#include "tsa_band.cuh"
 
 namespace tsa {
 
@@ -186,6 +187,10 @@ struct Engine::Impl {
     bool any_win = false;
     std::vector<int> h_winflag;
     DevBuf wave_prefix, wave_ticket;   // k_affine_wave: first ticket per pair, ticket counter
+    bool wave_ck = false;              // --no-ts with alignments through checkpoints (tsa_band.cuh: k_band_batch_*) instead of a code matrix
+    DevBuf bb_args, bb_ckpt, bb_colck, bb_res, bb_tiles, bb_bnds;
+    size_t bb_colck_bytes = 0;
+    int bb_trace_blocks = 0;
     size_t scratch_bytes = 0;
     int wave_tickets = 0;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
@@ -268,6 +273,13 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     for (auto& v : I.class_maxlen) v = 0;
     size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0, tab = 0;
     I.max_m = 0; I.max_n = 0;
+    I.wave_ck = false;
+    if (!I.ts_enabled && opt.traceback && n > 0 && opt.wave_checkpoints >= 0) {
+        // long pairs: checkpoints; short pairs: the code matrix is small and its walk needs no recomputation
+        double range_cells = 0;
+        for (size_t i = 0; i < n; i++) range_cells += (double)(pairs[i].rl - pairs[i].ro + 1) * (double)(pairs[i].ql - pairs[i].qo + 1);
+        I.wave_ck = opt.wave_checkpoints > 0 || range_cells / (double)n >= (double)(1 << 22);
+    }
     for (size_t i = 0; i < n; i++) {
         const PairView& pv = pairs[i];
         PairMeta& pm = I.metas[i];
@@ -296,7 +308,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
             tab += 4 * table_bytes(dev_.A, pm.lw);
         }
         if (I.ts_enabled) cells += (size_t)(pv.n + 1) * (pv.m + 1);
-        else if (opt.traceback) cells += (size_t)(pv.rl - pv.ro + 1) * (size_t)wave_dir_stride(pv.ql - pv.qo + 1);   // k_affine_wave: codes of the range, padded rows
+        else if (opt.traceback && !I.wave_ck) cells += (size_t)(pv.rl - pv.ro + 1) * (size_t)wave_dir_stride(pv.ql - pv.qo + 1);   // k_affine_wave: codes of the range, padded rows
         I.list_all.push_back((int)i);
     }
     if (!I.ts_enabled) {
@@ -311,6 +323,22 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         rt::h2d(I.wave_prefix.p, prefix.data(), prefix.size() * 4, I.stream);
         rt::stream_sync(I.stream);   // `prefix` is a local
     }
+    size_t bb_bytes = 0;
+    std::vector<size_t> bb_ckpt_off, bb_colck_off;
+    if (I.wave_ck) {
+        // per pair: checkpoint rows (3 ints per column, every BB_INTERVAL rows) and the boundary column entering every column group
+        size_t ck_ints = 0, col_entries = 0;
+        for (size_t k = 0; k < I.list_all.size(); k++) {
+            const PairView& pv = pairs[I.list_all[k]];
+            const size_t nn = (size_t)(pv.rl - pv.ro), mm = (size_t)(pv.ql - pv.qo);
+            bb_ckpt_off.push_back(ck_ints); bb_colck_off.push_back(col_entries);
+            ck_ints += std::max<size_t>(1, nn / BB_INTERVAL) * (mm + 2) * 3;
+            col_entries += (size_t)((wave_strips((int)mm + 1) + BB_GROUP - 1) / BB_GROUP) * (nn + 1);
+        }
+        bb_bytes = ck_ints * 4 + col_entries * 8;
+        I.bb_ckpt.ensure(ck_ints * 4); I.bb_colck.ensure(col_entries * 8); I.bb_colck_bytes = col_entries * 8;
+        I.bb_args.ensure(I.list_all.size() * sizeof(BandArgs)); I.bb_res.ensure(I.list_all.size() * 8);
+    }
     I.cells = cells;
     I.max_recs = std::min(opt.max_layers, MAX_TRACE_LAYERS);
     if (opt.traceback) {
@@ -323,7 +351,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         }
         I.ops_total = off;
     }
-    size_t need = seq_bytes + cells * (I.ts_enabled ? 12 : 0) + (opt.traceback ? cells * 3 + I.ops_total : 0) + vec * 4 + scr * 4 + n * (sizeof(PairMeta) + 32);
+    size_t need = seq_bytes + cells * (I.ts_enabled ? 12 : 0) + (opt.traceback ? cells * 3 + I.ops_total : 0) + vec * 4 + scr * 4 + n * (sizeof(PairMeta) + 32) + bb_bytes;
     if (need > opt.chunk_bytes && n > 1) return false;
     I.seqpool.resize(seq_bytes);
     for (size_t i = 0; i < n; i++) {
@@ -359,6 +387,28 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     rt::h2d(I.meta.p, I.metas.data(), n * sizeof(PairMeta), I.stream);
     rt::h2d(I.seq.p, I.seqpool.data(), seq_bytes, I.stream);
     stats_.h2d_bytes = (long long)(n * sizeof(PairMeta) + seq_bytes + flat.size() * 4);
+    if (I.wave_ck) {
+        std::vector<BandArgs> args(I.list_all.size());
+        for (size_t k = 0; k < I.list_all.size(); k++) {
+            const PairMeta& pm = I.metas[(size_t)I.list_all[k]];
+            BandArgs& ba = args[k];
+            memset(&ba, 0, sizeof(ba));
+            ba.R = I.seq.as<uint8_t>() + pm.seq_r + pm.ro; ba.Q = I.seq.as<uint8_t>() + pm.seq_q + pm.qo;
+            ba.nn = pm.rl - pm.ro; ba.mm = pm.ql - pm.qo;
+            ba.s_total = wave_strips(ba.mm + 1);
+            ba.s_lo = 0; ba.n_strips = ba.s_total; ba.s_band_first = 0; ba.s_band_last = ba.s_total - 1;
+            ba.group = BB_GROUP; ba.row0 = 0; ba.row1 = ba.nn; ba.ck_col0 = 0;
+            ba.ckpt_in = nullptr; ba.ckpt_out = I.bb_ckpt.as<int>() + bb_ckpt_off[k];
+            ba.interval = BB_INTERVAL; ba.ckpt_stride = ((long long)ba.mm + 2) * 3;
+            ba.colck = I.bb_colck.as<WaveBnd>() + bb_colck_off[k]; ba.colck_g0 = 0; ba.store_cols = 1;
+            ba.bnd_local = reinterpret_cast<WaveBnd*>(I.scratch.as<int>() + pm.scr); ba.bnd_out = nullptr;
+            ba.dir = nullptr; ba.dstride = 0; ba.row_base = 0;
+            ba.ticket = nullptr; ba.result = I.bb_res.as<int>() + 2 * k;
+        }
+        rt::h2d(I.bb_args.p, args.data(), args.size() * sizeof(BandArgs), I.stream);
+        rt::stream_sync(I.stream);   // `args` is a local
+        stats_.h2d_bytes += (long long)(args.size() * sizeof(BandArgs));
+    }
 
     Chunk& ck = I.ck;
     ck.pairs = I.meta.as<PairMeta>();
@@ -719,7 +769,7 @@ void Engine::run_wave() {
     Impl& I = *impl_;
     const int n_all = (int)I.list_all.size();
     if (n_all == 0 || I.wave_tickets == 0) return;
-    if (I.opt.traceback) {
+    if (I.opt.traceback && !I.wave_ck) {
         while (I.dirL.empty()) { I.dirL.push_back(new DevBuf); I.DL.push_back(new DevBuf); }
         I.dirL[0]->ensure(I.cells);
         I.ck.dir = I.dirL[0]->as<uint8_t>();
@@ -750,9 +800,23 @@ void Engine::run_wave() {
 #else
     blocks = std::min(blocks, 2);
 #endif
+    if (I.wave_ck) {
+        // forward pass with checkpoints (tsa_band.cuh); boundary columns start as "not written"
+        rt::dev_memset(I.bb_colck.p, 0xff, I.bb_colck_bytes, I.stream);
+        std::vector<int> res_init(2 * (size_t)n_all, 0);
+        for (int k = 0; k < n_all; k++) res_init[2 * (size_t)k] = INF32;
+        rt::h2d(I.bb_res.p, res_init.data(), res_init.size() * 4, I.stream);
+        rt::stream_sync(I.stream);   // `res_init` is a local
+        BandBatch bb;
+        bb.args = I.bb_args.as<BandArgs>(); bb.pair_of = I.d_list_all; bb.prefix = I.wave_prefix.as<int>(); bb.n_pairs = n_all; bb.ticket = I.wave_ticket.as<int>();
+        TSA_LAUNCH(k_band_batch_forward, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), smem, I.stream, I.cfg.as<DevConfig>(), bb);
+        TSA_LAUNCH(k_band_batch_finish, dim3((unsigned)((n_all + 255) / 256)), dim3(256), 0, I.stream, I.ck, bb);
+        stats_.launches += 2; stats_.fill_launches++;
+    } else {
     if (I.opt.traceback) TSA_LAUNCH(k_affine_wave<true>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), smem, I.stream, I.ck, wa);
     else TSA_LAUNCH(k_affine_wave<false>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), smem, I.stream, I.ck, wa);
     stats_.launches++; stats_.fill_launches++;
+    }
 #ifndef TSA_EMUL
     rt::check(cudaEventRecord(I.ev[1], I.stream), "cudaEventRecord");
     rt::check(cudaEventSynchronize(I.ev[1]), "cudaEventSynchronize");
@@ -800,7 +864,21 @@ void Engine::run_trace() {
     to.ops = I.ops.as<uint8_t>(); to.ops_off = I.ops_off.as<long long>(); to.ops_cap = I.ops_cap.as<int>(); to.ops_len = I.ops_len.as<int>();
     to.recs = I.recs.as<TsRecord>(); to.max_recs = I.max_recs; to.n_recs = I.n_recs.as<int>(); to.status = I.tstatus.as<int>();
     long long l = 0;
-    if (!I.ts_enabled) {
+    if (!I.ts_enabled && I.wave_ck) {
+        const int n_all = (int)I.list_all.size();
+        int blocks = std::max(1, std::min((n_all + WAVE_WARPS - 1) / WAVE_WARPS, 4 * 148));
+#ifdef TSA_EMUL
+        blocks = std::min(blocks, 2);
+#endif
+        const size_t warps = (size_t)blocks * WAVE_WARPS;
+        BandBatchTrace bt;
+        bt.tile_bytes = (long long)(BB_INTERVAL + 1) * BB_GROUP * WAVE_SW;
+        I.bb_tiles.ensure(warps * (size_t)bt.tile_bytes); I.bb_bnds.ensure(warps * (size_t)(BB_INTERVAL + 1) * sizeof(WaveBnd));
+        bt.tiles = I.bb_tiles.as<uint8_t>(); bt.bnds = I.bb_bnds.as<WaveBnd>();
+        BandBatch bb;
+        bb.args = I.bb_args.as<BandArgs>(); bb.pair_of = I.d_list_all; bb.prefix = I.wave_prefix.as<int>(); bb.n_pairs = n_all; bb.ticket = I.wave_ticket.as<int>();
+        if (n_all) { TSA_LAUNCH(k_band_batch_trace, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), (size_t)WAVE_SMEM_INTS * sizeof(int), I.stream, I.cfg.as<DevConfig>(), I.ck, bb, bt, to); l++; }
+    } else if (!I.ts_enabled) {
         launch_trace<3, false>(I.ck, tl, to, I.rows, I.d_list_all, (int)I.list_all.size(), 0, dev_.A, I.stream, l);
     } else {
         for (int c = 0; c < N_CLASS; c++) {

@@ -114,3 +114,20 @@ def test_batch_memory_limit_emulated(configs):
     ts = tsa.Aligner(costs=configs["sample"], lib=emul())
     got = ts.align_batch([small, (r[:400], q[:400]), small], memory_limit=1 << 20)
     assert [g.result_type for g in got] == ["FoundTarget", "ExceededMemoryLimit", "FoundTarget"] and got[1].status == 0 and got[1].ops is None
+
+
+def test_batch_checkpoints_emulated(configs):
+    # --no-ts batches with alignments through checkpoint rows + recomputed tiles (k_band_batch_*, what chunks of long pairs use on
+    # the GPU), forced here on short pairs: several tiles per pair, edge shapes, a range; and the code-matrix path on the same pairs
+    flat = oracle.FlatConfig(parse_config_any(configs["sample"]))
+    pairs = [workloads.long_pair(300 + k, n, sub_rate=s, indel_rate=d) for k, (n, s, d) in enumerate([(700, 0.05, 0.03), (1300, 0.1, 0.05), (300, 0.02, 0.01), (900, 0.3, 0.2)])]
+    pairs += [("ACGT" * 100, "ACGT" * 170), ("A" * 300, "C" * 10), ("", "ACGT" * 70), ("ACGT" * 70, ""), ("", "")]
+    ck = tsa.Aligner(costs=configs["sample"], no_ts=True, lib=emul(), dev_flags=8).align_batch(pairs)
+    codes = tsa.Aligner(costs=configs["sample"], no_ts=True, lib=emul(), dev_flags=16).align_batch(pairs)
+    for (r, q), g, c in zip(pairs, ck, codes):
+        _check(flat, r, q, g)
+        assert c.cost == g.cost
+    r, q = pairs[1]
+    rng = (100, 1200, 50, 1150)
+    res = tsa.Aligner(costs=configs["sample"], no_ts=True, lib=emul(), dev_flags=8).align_batch([(r, q, rng)])[0]
+    _check(flat, r, q, res, rng)
