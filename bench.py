@@ -257,9 +257,9 @@ def sub_records(which, lib, device, steps):
     if "c3" in which:
         try:
             ftext = text.replace("left_flank_length = 0", "left_flank_length = 50").replace("right_flank_length = 0", "right_flank_length = 50")
-            pairs = [workloads.long_pair(i, 1000, indel_rate=0.0, n_tsm=5) for i in range(32)]
+            pairs = [workloads.long_pair(i, 1000, indel_rate=0.0, n_tsm=5) for i in range(128)]
             out["c3"] = batch_record(tsa.Aligner(costs=ftext, device=device, lib=lib), pairs, lambda n, m, k: workloads.algorithmic_work(n, m, k, flank_planes=101), s16.value,
-                                     "k_flank_fused + k_primary_fill + k_ts_jump", "configs[2] shape: 32 synthetic 1 kb pairs per step, 5 planted TSMs, flank lengths 50 / 50, alignments returned")
+                                     "k_flank_fused + k_primary_fill + k_ts_jump", "configs[2] shape: 128 synthetic 1 kb pairs per step, 5 planted TSMs, flank lengths 50 / 50, alignments returned")
         except Exception as exc:  # noqa: BLE001
             out["c3"] = {"error": repr(exc)}
     return out

@@ -79,11 +79,12 @@ constexpr int KEY_PLANES = 512;   // tgt_key = cost * KEY_PLANES + plane index
 constexpr int KEY_INF = 0x7f7f7f7f;   // memset-able
 
 // One candidate row of a chain pair, handed from the row kernel (k_ts_jump<C, false, true>) to the evaluation kernel (k_ts_eval):
-// the start costs of the row's columns follow in Chunk::q_rows (32 * C packed words per slot).
+// the start costs of the row's live lanes follow in Chunk::q_rows (a slot of 32 * C packed words, used from the front).
 struct QueueHdr {
-    int kk;                  // kind index | flags << 8 (bit 0 / 1: the low / high chain can still produce a seed below the bound); < 0: reserved slot that was not used
+    int kk;                  // kind index | flags << 8 (bit 0 / 1: the low / high chain can still produce a seed below the bound) | entrance row << 12; < 0: reserved slot that was not used
     int b;                   // pair
-    int e0, ip;              // primary end of the low chain (the high chain ends at e0 + 1), entrance row
+    int e0;                  // primary end of the low chain (the high chain ends at e0 + 1)
+    int lanes;               // lanes whose columns are stored (packed to the front of the slot's row): those with a start cost below the bound
     int nbw;                 // packed, negated pruning bounds of the two chains: -(slack - rowmin D(ip) - length cost), 0: no exit from this row
     int lcw;                 // packed length costs of the two chains at this row (INF16: no exit)
     int msw;                 // packed cheapest start costs of the two chains at this row (lower bound of every jump-in)
