@@ -130,3 +130,35 @@ def test_batch_front_end(workdir, pairs):
     assert rows[1][1] == "pair1" and rows[1][3] == "FoundTarget" and rows[2][3] == "Error"
     odd = run(workdir, "align", "--pairs", "test_files/reference_a.fa")
     assert odd.returncode != 0 and "even number of records" in odd.stderr
+
+
+def test_toml_bytes_against_golden_no_ts(workdir, toml_golden, configs):
+    # Byte-level layout of the TOML result file against the reference's committed --no-ts result files (the TS files need the GPU:
+    # tests/test_gpu_parity.py::test_cli_toml_bytes_against_golden_gpu): every line that does not depend on the search statistics or
+    # on the tie-break among optimal alignments is identical text, in the same order.
+    from helpers import parse_config_any
+    volatile = ("duration_seconds", "opened_nodes", "closed_nodes", "suboptimal_opened_nodes", "suboptimal_opened_nodes_ratio", "runtime", "memory", "alignment")
+    checked = 0
+    for name, g in toml_golden.items():
+        p = g["parsed"]
+        if p["type"] != "WithTarget" or "no_ts" not in name:
+            continue
+        seqs = p["sequences"]
+        ocfg = parse_config_any(configs[g["config"]])
+        flat = oracle.FlatConfig(ocfg)
+        _, er, eq, ok = oracle.rescore(flat, seqs["reference"], seqs["query"], ops_from_toml(p["alignment"]), p["reference_offset"], p["query_offset"])
+        assert ok
+        d = workdir / ("bytes_" + name.replace(".toml", ""))
+        os.makedirs(d / "cfg", exist_ok=True)
+        (d / "cfg" / "config.tsa").write_text(configs[g["config"]])
+        (d / "pair.fa").write_text(f">{seqs['reference_name'].rstrip(' ')}\n{seqs['reference']}\n>{seqs['query_name'].rstrip(' ')}\n{seqs['query']}\n")
+        r = run(d, "align", "-p", "pair.fa", "-c", "cfg", "-a", ocfg.alphabet, "-o", "out.toml", "--dont-extend-beyond-range", "--no-ts",
+                "--rq-ranges", f"R{p['reference_offset']}..{er}Q{p['query_offset']}..{eq}")
+        assert r.returncode == 0, (name, r.stderr)
+        ours, gold = (d / "out.toml").read_text().splitlines(), g["raw"].splitlines()
+        assert [ln.split(" =")[0] for ln in ours] == [ln.split(" =")[0] for ln in gold], name
+        for a, b in zip(ours, gold):
+            if a.split(" =")[0] not in volatile:
+                assert a == b, (name, a[:120], b[:120])
+        checked += 1
+    assert checked >= 3

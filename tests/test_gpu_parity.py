@@ -394,3 +394,73 @@ def test_cli_binary_batch_gpu(lib, tmp_path):
     one = subprocess.run([cli, "align", "-p", "one.fa", "-c", "cfg", "-o", "one.toml"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert one.returncode == 0 and f"Reached target with cost {gold[ids[0]]['cost']}" in one.stdout, one.stderr
     assert "astar_result_type = \"FoundTarget\"" in (tmp_path / "one.toml").read_text()
+
+
+def test_cli_toml_bytes_against_golden_gpu(lib, configs, toml_golden, tmp_path):
+    # Byte-level layout of the TOML result file against the reference's committed result files (test_files/*.toml, written by
+    # toml 0.9 / noisy_float through align/template_switch_distance_type_selectors.rs:442-449): the real CLI binary is run on the
+    # file's sequences and range; every line that does not depend on the search statistics must be identical text, and where the
+    # returned alignment equals the recorded one the `alignment = [...]` line (inline tables of the entrances / exits) as well.
+    import os
+    import subprocess
+    import tomllib
+    from helpers import ops_from_toml
+    cli = os.path.join(os.path.dirname(os.path.abspath(_lib.LIB_PATH)), "tsalign-b200")
+    assert os.path.exists(cli)
+    volatile = ("duration_seconds", "opened_nodes", "closed_nodes", "suboptimal_opened_nodes", "suboptimal_opened_nodes_ratio", "runtime", "memory")
+
+    def fmt_alignment(al):
+        out = []
+        for count, op in al:
+            if isinstance(op, str):
+                out.append(f'[{count}, "{op}"]')
+            elif "TemplateSwitchEntrance" in op:
+                e = op["TemplateSwitchEntrance"]
+                r = e["equal_cost_range"]
+                out.append(f'[{count}, {{ TemplateSwitchEntrance = {{ first_offset = {e["first_offset"]}, equal_cost_range = {{ min_start = {r["min_start"]}, max_start = {r["max_start"]}, '
+                           f'min_end = {r["min_end"]}, max_end = {r["max_end"]} }}, primary = "{e["primary"]}", secondary = "{e["secondary"]}", direction = "{e["direction"]}" }} }}]')
+            else:
+                out.append(f'[{count}, {{ TemplateSwitchExit = {{ anti_primary_gap = {op["TemplateSwitchExit"]["anti_primary_gap"]} }} }}]')
+        return "alignment = [" + ", ".join(out) + "]"
+
+    compared_alignments = compared_files = 0
+    for name, g in toml_golden.items():
+        p = g["parsed"]
+        if p["type"] != "WithTarget" or name.startswith("twin_ari"):      # (twin_ari: see DESIGN.md section 2, not an optimum of the sample model)
+            continue
+        seqs = p["sequences"]
+        ocfg = parse_config_any(configs[g["config"]])
+        flat = oracle.FlatConfig(ocfg)
+        _, er, eq, ok = oracle.rescore(flat, seqs["reference"], seqs["query"], ops_from_toml(p["alignment"]), p["reference_offset"], p["query_offset"])
+        assert ok
+        d = tmp_path / name.replace(".toml", "")
+        os.makedirs(d / "cfg")
+        (d / "cfg" / "config.tsa").write_text(configs[g["config"]])
+        rn, qn = seqs["reference_name"], seqs["query_name"]       # "<id> <comment>" (align.rs:418-419)
+        (d / "pair.fa").write_text(f">{rn.rstrip(' ') if rn.endswith(' ') and ' ' not in rn[:-1] else rn}\n{seqs['reference']}\n>{qn.rstrip(' ') if qn.endswith(' ') and ' ' not in qn[:-1] else qn}\n{seqs['query']}\n")
+        args = [cli, "align", "-p", "pair.fa", "-c", "cfg", "-a", ocfg.alphabet, "-o", "out.toml", "--dont-extend-beyond-range",
+                "--rq-ranges", f"R{p['reference_offset']}..{er}Q{p['query_offset']}..{eq}"]
+        if "no_ts" in name:
+            args.append("--no-ts")
+        run = subprocess.run(args, cwd=d, capture_output=True, text=True, timeout=900)
+        assert run.returncode == 0, (name, run.stderr)
+        ours_raw = (d / "out.toml").read_text()
+        ours = tomllib.loads(ours_raw)
+        if int(ours["cost"]) != int(p["cost"]):
+            continue                                                # (an optimum below the recorded cost: covered by test_golden_toml_costs_gpu)
+        ours_lines, gold_lines = ours_raw.splitlines(), g["raw"].splitlines()
+        assert [ln.split(" =")[0] for ln in ours_lines] == [ln.split(" =")[0] for ln in gold_lines], name      # same keys, same order, same sections
+        for a, b in zip(ours_lines, gold_lines):
+            key = a.split(" =")[0]
+            if key in volatile:
+                continue
+            if key == "alignment":
+                # one formatter must reproduce both lines byte for byte from their parsed values: same inline-table layout
+                assert a == fmt_alignment(ours["alignment"]) and b == fmt_alignment(p["alignment"]), (name, a[:200], b[:200])
+                compared_alignments += 1
+                if ours["alignment"] == p["alignment"]:
+                    assert a == b
+                continue
+            assert a == b, (name, a[:120], b[:120])
+        compared_files += 1
+    assert compared_files >= 4 and compared_alignments >= 1, (compared_files, compared_alignments)
