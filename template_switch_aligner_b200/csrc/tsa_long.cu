@@ -5,6 +5,8 @@
 #include <chrono>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <vector>
 #include <stdexcept>
 
 #include "tsa_band.cuh"
@@ -13,11 +15,50 @@
 namespace tsa {
 
 namespace {
+// Device buffers of a LongPair come from a small per-device cache and go back to it: cudaMalloc / cudaFree of a few hundred MB cost
+// tens to hundreds of milliseconds in a process that holds other large allocations -- as much as the alignment of the pair itself.
+struct BufCache {
+    struct Item { int device; void* p; size_t cap; };
+    std::mutex lock;
+    std::vector<Item> items;
+    size_t total = 0;
+    static BufCache& get() { static BufCache c; return c; }
+    static int device() {
+#ifndef TSA_EMUL
+        int d = 0; cudaGetDevice(&d); return d;
+#else
+        return 0;
+#endif
+    }
+    void* take(size_t bytes, size_t& cap) {
+        const int dev = device();
+        {
+            std::lock_guard<std::mutex> g(lock);
+            int best = -1;
+            for (size_t k = 0; k < items.size(); k++)
+                if (items[k].device == dev && items[k].cap >= bytes && items[k].cap <= 2 * bytes + (1 << 20) && (best < 0 || items[k].cap < items[(size_t)best].cap)) best = (int)k;
+            if (best >= 0) { Item it = items[(size_t)best]; items.erase(items.begin() + best); total -= it.cap; cap = it.cap; return it.p; }
+        }
+        cap = bytes;
+        return rt::dev_alloc(bytes);
+    }
+    void give(void* p, size_t cap) {
+        if (!p) return;
+        std::vector<Item> drop;
+        {
+            std::lock_guard<std::mutex> g(lock);
+            items.push_back(Item{device(), p, cap});
+            total += cap;
+            while (total > ((size_t)2 << 30) && !items.empty()) { drop.push_back(items.front()); total -= items.front().cap; items.erase(items.begin()); }   // at most 2 GiB kept
+        }
+        for (const Item& it : drop) rt::dev_free(it.p);
+    }
+};
 struct Buf {
     void* p = nullptr;
-    size_t cap = 0;
-    void ensure(size_t bytes) { if (bytes > cap) { rt::dev_free(p); p = rt::dev_alloc(bytes); cap = bytes; } }
-    ~Buf() { rt::dev_free(p); }
+    size_t cap = 0, used = 0;      // capacity of the (possibly cached, larger) allocation; bytes this object asked for
+    void ensure(size_t bytes) { if (bytes > cap) { BufCache::get().give(p, cap); p = BufCache::get().take(bytes, cap); } used = std::max(used, bytes); }
+    ~Buf() { BufCache::get().give(p, cap); }
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
 constexpr long long SMALL_INTS = 16;   // [0] ticket, [2..3] result, [4] ops_len, [8..] WalkState
@@ -138,10 +179,10 @@ LongPair::LongPair(const HostConfig& cfg, int device, const uint8_t* R, const ui
         I.ops.ensure(I.ops_cap);
     }
     // boundary entries start as "not written" (tag 4095); the rank on the left may start writing as soon as every rank is built
-    rt::dev_memset(I.colck.p, 0xff, I.colck.cap, I.stream);
+    rt::dev_memset(I.colck.p, 0xff, I.colck.used, I.stream);
     rt::dev_memset(I.bnd_local.p, 0xff, col_bytes, I.stream);
     rt::stream_sync(I.stream);
-    stats_.resident_bytes = (long long)(I.cfg.cap + I.R.cap + I.Q.cap + I.bnd_local.cap + I.colck.cap + I.small.cap + I.ckpt.cap + I.tile.cap + I.ops.cap);
+    stats_.resident_bytes = (long long)(I.cfg.used + I.R.used + I.Q.used + I.bnd_local.used + I.colck.used + I.small.used + I.ckpt.used + I.tile.used + I.ops.used);
     stats_.interval = plan.interval; stats_.group = plan.group;
     ok_ = true;
 }
@@ -279,6 +320,7 @@ LongResult align_long(const HostConfig& cfg, const int* devices, int n_devices, 
     world = std::min(world, std::max(1, wave_strips(mm + 1)));
     res.plan = plan_bands(nn, mm, world, interval, group, memory_limit, traceback);
     if (!res.plan.ok) { res.status = PAIR_OK; res.memory_limit_hit = true; res.message = res.plan.why; return res; }
+    const auto dbg_t0 = std::chrono::steady_clock::now();
     std::vector<std::unique_ptr<LongPair>> lp;
     for (int r = 0; r < world; r++) {
         lp.emplace_back(new LongPair(cfg, devices ? devices[r] : 0, R, Q, res.plan, r, traceback));
@@ -298,6 +340,7 @@ LongResult align_long(const HostConfig& cfg, const int* devices, int n_devices, 
         }
     }
 #endif
+    const auto dbg_t1 = std::chrono::steady_clock::now();
     for (int r = 0; r + 1 < world; r++) lp[r]->set_outgoing_boundary(lp[r + 1]->incoming_boundary());
     for (int r = 0; r < world; r++) lp[r]->forward_launch();
     for (int r = 0; r < world; r++) lp[r]->forward_wait();
@@ -322,6 +365,11 @@ LongResult align_long(const HostConfig& cfg, const int* devices, int n_devices, 
         res.ops.assign(rev.rbegin(), rev.rend());
     }
     for (int r = 0; r < world; r++) res.stats.push_back(lp[r]->stats());
+    const auto dbg_t2 = std::chrono::steady_clock::now();
+    lp.clear();
+    if (getenv("TSA_B200_DEBUG"))
+        fprintf(stderr, "[tsalign_b200] align_long: setup %.1f ms, forward + traceback %.1f ms, release %.1f ms\n", 1e3 * std::chrono::duration<double>(dbg_t1 - dbg_t0).count(),
+                1e3 * std::chrono::duration<double>(dbg_t2 - dbg_t1).count(), 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - dbg_t2).count());
     return res;
 }
 
