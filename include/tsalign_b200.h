@@ -159,6 +159,8 @@ typedef struct {
     int64_t boundary_bytes_out;        /* bytes this band stored into the next device's memory (8 per row) */
     int64_t resident_bytes;            /* device memory the band held */
     int32_t interval, group;           /* rows between checkpoint rows / 256-column strips between kept boundary columns */
+    int64_t speculated_tiles, speculated_used; /* tiles around the diagonal recomputed ahead of the walk in one launch, and how many the walk used */
+    double speculate_ms;               /* device time of that launch */
 } tsa_long_stats;
 /* All bands driven by this process (one host thread; devices[k] = CUDA device of band k, neighbours need peer access).
  * interval / group: 0 = chosen by the library.  stats: n_devices entries or NULL.  opt->no_ts must be set. */

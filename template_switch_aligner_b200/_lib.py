@@ -68,7 +68,8 @@ class TsaError(RuntimeError):
 
 class TsaLongStats(C.Structure):
     _fields_ = [("forward_ms", C.c_double), ("trace_ms", C.c_double), ("tiles", C.c_int64), ("tile_cells", C.c_int64),
-                ("boundary_bytes_out", C.c_int64), ("resident_bytes", C.c_int64), ("interval", C.c_int32), ("group", C.c_int32)]
+                ("boundary_bytes_out", C.c_int64), ("resident_bytes", C.c_int64), ("interval", C.c_int32), ("group", C.c_int32),
+                ("speculated_tiles", C.c_int64), ("speculated_used", C.c_int64), ("speculate_ms", C.c_double)]
 
 
 class TsaLongWalkState(C.Structure):

@@ -444,7 +444,8 @@ class StagedBatch:
 # ---- one very long pair without template switches, column-banded over several GPUs (tsa_align_long / tsa_long_*) ------------------
 def _long_stats(s) -> dict:
     return {"forward_ms": s.forward_ms, "trace_ms": s.trace_ms, "tiles": s.tiles, "tile_cells": s.tile_cells,
-            "boundary_bytes_out": s.boundary_bytes_out, "resident_bytes": s.resident_bytes, "interval": s.interval, "group": s.group}
+            "boundary_bytes_out": s.boundary_bytes_out, "resident_bytes": s.resident_bytes, "interval": s.interval, "group": s.group,
+            "speculated_tiles": s.speculated_tiles, "speculated_used": s.speculated_used, "speculate_ms": s.speculate_ms}
 
 
 def align_long(aligner: Aligner, reference, query, *, devices: Optional[Sequence[int]] = None, interval: int = 0, group: int = 0,

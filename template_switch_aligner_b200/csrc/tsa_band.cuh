@@ -348,7 +348,10 @@ struct BandBatch {
     int* ticket;
 };
 
-static TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_band_batch_forward(const DevConfig* cfg, BandBatch bb) {
+// TRACE = false: forward passes of many pairs.  TRACE = true: many TILES (of one pair or several) recomputed with codes at once --
+// every entry of bb.args is then one tile (row block x column group) with its own code and boundary buffers.
+template <bool TRACE>
+TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_band_batch(const DevConfig* cfg, BandBatch bb) {
     TSA_SHARED_DECL(smem_raw);
     int* subP = reinterpret_cast<int*>(smem_raw);
     int* openP = subP + MAX_ALPHABET * MAX_ALPHABET;
@@ -363,7 +366,7 @@ static TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM
         if (tk >= total) break;
         int lo = 0, hi = bb.n_pairs - 1;                           // last pair whose first ticket is <= tk
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (bb.prefix[mid] <= tk) lo = mid; else hi = mid - 1; }
-        band_strip<false>(bb.args[lo], tk - bb.prefix[lo], cfg->A, subP, openP, extP);      // (the description stays in global memory: its fields are read once per strip)
+        band_strip<TRACE>(bb.args[lo], bb.args[lo].s_lo + tk - bb.prefix[lo], cfg->A, subP, openP, extP);      // (the description stays in global memory: its fields are read once per strip)
     }
 }
 

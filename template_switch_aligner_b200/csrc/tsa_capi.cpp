@@ -572,6 +572,7 @@ int encode_long(const HostConfig& host, const tsa_pair* pair, Encoded& enc, std:
 void long_stats_out(const BandStats& b, tsa_long_stats& o) {
     o.forward_ms = b.forward_ms; o.trace_ms = b.trace_ms; o.tiles = b.tiles; o.tile_cells = b.tile_cells;
     o.boundary_bytes_out = b.boundary_bytes_out; o.resident_bytes = b.resident_bytes; o.interval = b.interval; o.group = b.group;
+    o.speculated_tiles = b.speculated_tiles; o.speculated_used = b.speculated_used; o.speculate_ms = b.speculate_ms;
 }
 
 // unit ops in path order -> tsa_result (run-length encoded), range of the pair
@@ -699,6 +700,15 @@ int tsa_long_forward(tsa_long* b) try {
     if (!b) return TSA_ERR_ARGUMENT;
     b->band->forward_launch();
     b->band->forward_wait();
+    if (b->opt.no_traceback == 0) {
+        // tiles around the diagonal recomputed ahead of the walk, under what the memory limit leaves (tsa_long.hpp: speculate)
+        size_t budget = (size_t)16 << 30;
+        if (b->opt.memory_limit != UINT64_MAX) {
+            const long long used = b->plan.resident_bytes(b->band->rank(), true);
+            budget = (long long)b->opt.memory_limit > used ? std::min<size_t>(budget, (size_t)((long long)b->opt.memory_limit - used)) : 0;
+        }
+        b->band->speculate(budget);
+    }
     return TSA_OK;
 } catch (const std::exception& e) {
     fprintf(stderr, "tsalign_b200: %s\n", e.what());

@@ -809,7 +809,7 @@ void Engine::run_wave() {
         rt::stream_sync(I.stream);   // `res_init` is a local
         BandBatch bb;
         bb.args = I.bb_args.as<BandArgs>(); bb.pair_of = I.d_list_all; bb.prefix = I.wave_prefix.as<int>(); bb.n_pairs = n_all; bb.ticket = I.wave_ticket.as<int>();
-        TSA_LAUNCH(k_band_batch_forward, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), smem, I.stream, I.cfg.as<DevConfig>(), bb);
+        TSA_LAUNCH(k_band_batch<false>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), smem, I.stream, I.cfg.as<DevConfig>(), bb);
         TSA_LAUNCH(k_band_batch_finish, dim3((unsigned)((n_all + 255) / 256)), dim3(256), 0, I.stream, I.ck, bb);
         stats_.launches += 2; stats_.fill_launches++;
     } else {

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -64,6 +65,9 @@ struct Buf {
 constexpr long long SMALL_INTS = 16;   // [0] ticket, [2..3] result, [4] ops_len, [8..] WalkState
 }  // namespace
 
+// Half width of the strip of tiles around the straight line from the root to the target that speculate() recomputes ahead of the walk.
+static int spec_margin(int nn, int mm) { return std::max(nn, mm) / 64 + WAVE_SW; }
+
 int BandPlan::owner_of_column(int j) const {
     const int gi = (j < 0 ? 0 : j / WAVE_SW) / group;
     int r = (int)(((long long)gi + 1) * world / n_groups);   // first guess, then correct
@@ -110,11 +114,17 @@ BandPlan plan_bands(int nn, int mm, int world, int interval, int group, size_t m
         long long worst = 0;
         for (int r = 0; r < world; r++) worst = std::max(worst, p.resident_bytes(r, traceback));
         if (memory_limit && (unsigned long long)worst > memory_limit) continue;
-        // time model of the traceback (measured on a B200, profiles/r02_c5_*): a path crosses ~nn / interval + columns / (256 group)
-        // tiles; a tile costs a fixed host round trip plus the wavefront latency of its rows and of its pipeline of strips
-        const double tiles = (double)nn / ci + (double)mm / ((double)cg * WAVE_SW) + world;
+        // time model of the traceback (measured on a B200, profiles/r02_c5_*).  A path crosses ~nn / interval + columns / (256 group)
+        // tiles.  If the code buffers of the tiles around the diagonal fit (speculate()), they are recomputed in one launch -- the
+        // slower of one tile's wavefront latency and their cells at ~400 GCUPS -- and every crossed tile costs one host round trip of
+        // the walk; else a crossed tile costs a round trip plus its own wavefront latency.
+        const double crossed = (double)nn / ci + (double)mm / ((double)cg * WAVE_SW) + world;
+        const double margin = (double)spec_margin(nn, mm);
+        const double diag_tiles = ((double)nn / ci + 1.0) * (std::floor(((double)ci * mm / std::max(nn, 1) + 2.0 * margin) / ((double)cg * WAVE_SW)) + 2.0);
+        const double spec_bytes = diag_tiles * ((double)ci + 1.0) * cg * WAVE_SW / world;
+        const bool can_spec = spec_bytes <= (double)((size_t)16 << 30) && (memory_limit == 0 || (double)worst + spec_bytes <= (double)memory_limit);
         const double t_tile = 120.0 + std::max(0.16 * ((double)ci + 32.0 * cg), (double)ci * cg * WAVE_SW / 4.0e5);   // microseconds
-        const double score = tiles * t_tile;
+        const double score = can_spec ? crossed * 150.0 + std::max(0.4 * ((double)ci + 40.0 * cg), spec_bytes / 4.0e5) : crossed * t_tile;
         if (best_score < 0 || score < best_score) { best_score = score; p.ok = true; best = p; }
     }
     if (!best.ok) best.why = "no checkpoint spacing fits the memory limit";
@@ -124,6 +134,10 @@ BandPlan plan_bands(int nn, int mm, int world, int interval, int group, size_t m
 struct LongPair::Impl {
     cudaStream_t stream = 0;
     Buf cfg, R, Q, colck, bnd_local, ckpt, tile, ops, small;
+    Buf sp_codes, sp_bnds, sp_args, sp_prefix;          // speculate(): codes / boundaries / descriptions of the tiles recomputed ahead
+    std::vector<std::pair<int, int>> sp_tiles;          // (row block, first strip of the group) of every speculated tile, in buffer order
+    size_t sp_tile_bytes = 0;
+    bool sp_pending = false;
     WaveBnd* bnd_out = nullptr;
     int s_first = 0, s_last = 0, g_first = 0, n_groups = 0, bw = 0;
     long long ckpt_stride = 0, dstride = 0;
@@ -249,6 +263,80 @@ void LongPair::forward_wait() {
     if (has_target()) cost_ = h[2];
 }
 
+void LongPair::speculate(size_t budget_bytes) {
+    Impl& I = *impl_;
+    if (!traceback_ || !ok_) return;
+#ifndef TSA_EMUL
+    rt::check(cudaSetDevice(device_), "cudaSetDevice");
+#endif
+    const int nn = plan_.nn, mm = plan_.mm, IV = plan_.interval, G = plan_.group;
+    const size_t tile_bytes = (size_t)(IV + 1) * (size_t)I.dstride;
+    const size_t per_tile = tile_bytes + (size_t)(IV + 1) * sizeof(WaveBnd) + sizeof(BandArgs) + 8;
+    const size_t max_tiles = std::min<size_t>(budget_bytes / std::max<size_t>(1, per_tile), 4096);
+    // tiles that the straight line from (0, 0) to (nn, mm) crosses, widened by 1/64 of the pair + one strip on either side
+    std::vector<std::pair<int, int>> tiles;
+    const int margin = spec_margin(nn, mm);
+    for (int k = 0; k * IV < std::max(nn, 1); k++) {
+        const long long r0 = (long long)k * IV, r1 = std::min<long long>(r0 + IV, nn);
+        const long long j_lo = std::max<long long>(0, (nn ? r0 * mm / nn : 0) - margin), j_hi = std::min<long long>(mm, (nn ? r1 * mm / nn : mm) + margin);
+        for (int g = (int)(j_lo / WAVE_SW) / G; g <= (int)(j_hi / WAVE_SW) / G; g++) {
+            const int s_lo = g * G;
+            if (s_lo < I.s_first || s_lo > I.s_last) continue;      // another band's tile
+            tiles.emplace_back(k, s_lo);
+        }
+    }
+    // the tiles nearest to the target first (the walk starts there), as many as the budget holds
+    std::reverse(tiles.begin(), tiles.end());
+    if (tiles.size() > max_tiles) tiles.resize(max_tiles);
+    if (tiles.empty()) return;
+    const size_t T = tiles.size();
+    I.sp_tile_bytes = tile_bytes;
+    I.sp_codes.ensure(T * tile_bytes);
+    I.sp_bnds.ensure(T * (size_t)(IV + 1) * sizeof(WaveBnd));
+    I.sp_args.ensure(T * sizeof(BandArgs));
+    I.sp_prefix.ensure((T + 2) * sizeof(int));
+    std::vector<BandArgs> args(T);
+    std::vector<int> prefix(T + 2, 0);
+    for (size_t t = 0; t < T; t++) {
+        const int k = tiles[t].first, s_lo = tiles[t].second;
+        BandArgs& ba = args[t];
+        memset(&ba, 0, sizeof(ba));
+        const int row0 = k * IV, row1 = std::min(row0 + IV, nn);
+        const int s_hi = std::min(std::min(s_lo + G - 1, I.s_last), plan_.s_total - 1);
+        ba.R = I.R.as<uint8_t>(); ba.Q = I.Q.as<uint8_t>(); ba.nn = nn; ba.mm = mm;
+        ba.s_lo = s_lo; ba.n_strips = s_hi - s_lo + 1; ba.s_total = plan_.s_total; ba.s_band_first = I.s_first; ba.s_band_last = I.s_last;
+        ba.group = G; ba.row0 = row0; ba.row1 = row1; ba.ck_col0 = col_first_;
+        ba.ckpt_in = k > 0 ? I.ckpt.as<int>() + (long long)(k - 1) * I.ckpt_stride : nullptr;
+        ba.ckpt_out = nullptr; ba.interval = IV; ba.ckpt_stride = I.ckpt_stride;
+        ba.colck = I.colck.as<WaveBnd>(); ba.colck_g0 = I.g_first; ba.store_cols = 0;
+        ba.bnd_local = I.sp_bnds.as<WaveBnd>() + (long long)t * (IV + 1) - row0;      // indexed by the absolute row
+        ba.bnd_out = nullptr;
+        ba.dir = I.sp_codes.as<uint8_t>() + t * tile_bytes; ba.dstride = I.dstride; ba.row_base = k > 0 ? row0 + 1 : 0;
+        ba.ticket = nullptr; ba.result = I.small.as<int>() + 2;
+        prefix[t + 1] = prefix[t] + ba.n_strips;
+    }
+    prefix[T + 1] = 0;      // the ticket
+    rt::h2d(I.sp_args.p, args.data(), T * sizeof(BandArgs), I.stream);
+    rt::h2d(I.sp_prefix.p, prefix.data(), (T + 2) * sizeof(int), I.stream);
+    rt::dev_memset(I.sp_bnds.p, 0xff, T * (size_t)(IV + 1) * sizeof(WaveBnd), I.stream);
+    rt::stream_sync(I.stream);   // `args`, `prefix` are locals
+    BandBatch bb;
+    bb.args = I.sp_args.as<BandArgs>(); bb.pair_of = nullptr; bb.prefix = I.sp_prefix.as<int>(); bb.n_pairs = (int)T; bb.ticket = I.sp_prefix.as<int>() + T + 1;
+    const int blocks = std::min(I.resident_blocks, (prefix[T] + WAVE_WARPS - 1) / WAVE_WARPS);
+#ifndef TSA_EMUL
+    rt::check(cudaEventRecord(I.ev[0], I.stream), "cudaEventRecord");
+#endif
+    TSA_LAUNCH(k_band_batch<true>, dim3((unsigned)std::max(1, blocks)), dim3(32 * WAVE_WARPS), (size_t)WAVE_SMEM_INTS * sizeof(int), I.stream, I.cfg.as<DevConfig>(), bb);
+#ifndef TSA_EMUL
+    rt::check(cudaEventRecord(I.ev[1], I.stream), "cudaEventRecord");
+#endif
+    I.sp_tiles = tiles;
+    I.sp_pending = true;
+    stats_.speculated_tiles = (long long)T;
+    stats_.resident_bytes += (long long)(I.sp_codes.used + I.sp_bnds.used + I.sp_args.used + I.sp_prefix.used);
+    for (size_t t = 0; t < T; t++) stats_.tile_cells += (long long)(args[t].row1 - args[t].row0 + 1) * (long long)args[t].n_strips * WAVE_SW;
+}
+
 BandWalk LongPair::walk(const BandWalk& in, std::vector<uint8_t>& ops_rev) {
     Impl& I = *impl_;
     BandWalk st = in;
@@ -264,6 +352,17 @@ BandWalk LongPair::walk(const BandWalk& in, std::vector<uint8_t>& ops_rev) {
         const int row0 = k * IV, row1 = st.i;
         const int s_hi = st.j / WAVE_SW, s_lo = (s_hi / G) * G;
         if (s_hi > I.s_last || s_lo < I.s_first) { st.status = WALK_ERR; break; }
+        int spec = -1;
+        for (size_t t = 0; t < I.sp_tiles.size(); t++) if (I.sp_tiles[t].first == k && I.sp_tiles[t].second == s_lo) { spec = (int)t; break; }
+        if (spec >= 0 && I.sp_pending) {
+#ifndef TSA_EMUL
+            rt::check(cudaEventSynchronize(I.ev[1]), "speculative tiles");
+            float ms = 0; cudaEventElapsedTime(&ms, I.ev[0], I.ev[1]);
+            stats_.speculate_ms = ms;
+#endif
+            rt::stream_sync(I.stream);
+            I.sp_pending = false;
+        }
         int init[SMALL_INTS] = {0};
         WalkState ws;
         ws.i = st.i; ws.j = st.j; ws.g = st.g; ws.need = st.need; ws.cost = st.cost; ws.status = WALK_GOING; ws.pad = 0;
@@ -282,7 +381,12 @@ BandWalk LongPair::walk(const BandWalk& in, std::vector<uint8_t>& ops_rev) {
         ba.dir = I.tile.as<uint8_t>(); ba.dstride = I.dstride; ba.row_base = k > 0 ? row0 + 1 : 0;
         ba.ticket = I.small.as<int>(); ba.result = I.small.as<int>() + 2;
         const int blocks = std::min(I.resident_blocks, (ba.n_strips + WAVE_WARPS - 1) / WAVE_WARPS);
-        TSA_LAUNCH(k_affine_band<true>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), (size_t)WAVE_SMEM_INTS * sizeof(int), I.stream, I.cfg.as<DevConfig>(), ba);
+        if (spec >= 0) {
+            ba.dir = I.sp_codes.as<uint8_t>() + (size_t)spec * I.sp_tile_bytes;      // recomputed ahead (the whole tile: a superset of what this walk needs)
+            stats_.speculated_used++;
+        } else {
+            TSA_LAUNCH(k_affine_band<true>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), (size_t)WAVE_SMEM_INTS * sizeof(int), I.stream, I.cfg.as<DevConfig>(), ba);
+        }
         WalkArgs wa;
         memset(&wa, 0, sizeof(wa));
         wa.R = ba.R; wa.Q = ba.Q; wa.dir = ba.dir; wa.dstride = ba.dstride; wa.row_base = ba.row_base; wa.col_base = s_lo * WAVE_SW;
@@ -298,8 +402,10 @@ BandWalk LongPair::walk(const BandWalk& in, std::vector<uint8_t>& ops_rev) {
         const bool moved = ws.i != st.i || ws.j != st.j || ws.need != st.need || ws.g != st.g || ws.status != WALK_GOING;
         st.i = ws.i; st.j = ws.j; st.g = ws.g; st.need = ws.need; st.cost = ws.cost; st.status = ws.status;
         pos += (size_t)h[4];
-        stats_.tiles++;
-        stats_.tile_cells += (long long)(row1 - row0 + 1) * (long long)ba.n_strips * WAVE_SW;
+        if (spec < 0) {
+            stats_.tiles++;
+            stats_.tile_cells += (long long)(row1 - row0 + 1) * (long long)ba.n_strips * WAVE_SW;
+        }
         if (!moved) { st.status = WALK_ERR; break; }
     }
     if (pos) {
@@ -344,6 +450,14 @@ LongResult align_long(const HostConfig& cfg, const int* devices, int n_devices, 
     for (int r = 0; r + 1 < world; r++) lp[r]->set_outgoing_boundary(lp[r + 1]->incoming_boundary());
     for (int r = 0; r < world; r++) lp[r]->forward_launch();
     for (int r = 0; r < world; r++) lp[r]->forward_wait();
+    if (traceback) {
+        // code buffers for tiles recomputed ahead of the walk: what the memory limit leaves on every device, at most 16 GiB
+        for (int r = 0; r < world; r++) {
+            size_t budget = (size_t)16 << 30;
+            if (memory_limit) { const long long used = res.plan.resident_bytes(r, true); budget = (long long)memory_limit > used ? std::min<size_t>(budget, (size_t)((long long)memory_limit - used)) : 0; }
+            lp[r]->speculate(budget);
+        }
+    }
     bool sat = false;
     for (int r = 0; r < world; r++) sat = sat || lp[r]->saturated();
     res.cost = lp[world - 1]->cost();

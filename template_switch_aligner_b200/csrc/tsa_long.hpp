@@ -23,6 +23,8 @@ struct BandWalk {            // mirror of WalkState (tsa_band.cuh) for the calle
 struct BandStats {
     double forward_ms = 0, trace_ms = 0;         // device time of the forward launch (CUDA events); host wall time of the walks
     long long tiles = 0, tile_cells = 0;         // tiles recomputed by the traceback and their cells
+    long long speculated_tiles = 0, speculated_used = 0;   // tiles recomputed ahead of the walk, all at once (speculate()), and how many the walk used
+    double speculate_ms = 0;
     long long boundary_bytes_out = 0;            // bytes stored into the next rank's memory by the forward pass (8 per row)
     long long resident_bytes = 0;                // device memory held by this band
     int interval = 0, group = 0;
@@ -64,6 +66,11 @@ public:
 
     void forward_launch();                            // fill of the band; asynchronous (the bands of all ranks run as one pipeline)
     void forward_wait();
+    // Recompute, with codes, the tiles around the straight line from the root to the target that lie in this band -- all of them in ONE
+    // launch (every tile only needs the checkpoint row above it and the boundary column to its left, both kept by the forward pass), as
+    // many as `budget_bytes` of code buffers allow.  The walk then only recomputes a tile on its own when the path leaves that set:
+    // the traceback of a long pair costs one tile latency instead of one per tile crossed.  Asynchronous; walk() waits.
+    void speculate(size_t budget_bytes);
     bool has_target() const { return rank_ == plan_.world - 1; }
     long long cost() const { return cost_; }          // has_target() only; >= INF32: no target
     bool saturated() const { return saturated_; }
