@@ -432,14 +432,14 @@ def run_ours(args):
     # scaled to the pairs of one launch here; nothing is measured under a profiler in this run
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_k_ts_jump5_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_k_ts_jump_traffic.json")) as fh:
             tr = json.load(fh)
         traffic = (tr["dram_read_bytes"] + tr["dram_write_bytes"]) / tr["pairs_in_launch"] * batch
         traffic_src = tr["source"]
     except (OSError, KeyError, ValueError):
         pass
-    roofline = {"bound": "integer (DPX add-min, packed s16x2 lanes)", "kernel": "k_ts_jump<5,false>", "achieved": achieved, "peak": peak, "unit": "Tadd-min/s",
-                "frac": (achieved / peak) if achieved and peak else None, "traffic": traffic, "traffic_unit": "bytes per layer-0 launch (dram read + write)",
+    roofline = {"bound": "integer (DPX add-min, packed s16x2 lanes)", "kernel": "k_ts_jump<5,false,true> (row kernel) + k_ts_eval<5> (evaluation kernel)", "achieved": achieved, "peak": peak, "unit": "Tadd-min/s",
+                "frac": (achieved / peak) if achieved and peak else None, "traffic": traffic, "traffic_unit": "bytes per layer-0 launch of the two kernels (dram read + write), scaled from the profiled batch to this one",
                 "traffic_source": traffic_src,
                 "peak_source": "measured in this run by tsa_measure_addmin_peak (back-to-back __viaddmin_s16x2 on all SMs); s32 rate %.2f T/s" % (s32.value / 1e12),
                 "algorithmic_ops_per_launch": w_jump * args.steps / jl, "avg_launch_ms": jump_ms / jl,
