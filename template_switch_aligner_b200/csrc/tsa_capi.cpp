@@ -144,7 +144,7 @@ void fill_result(tsa_result& r, const PairCost& pc, const tsa_options& opt) {
         break;
     case PAIR_NO_TARGET: r.status = TSA_OK; r.result_type = TSA_NO_TARGET; break;
     case PAIR_MEMORY_LIMIT: r.status = TSA_OK; r.result_type = TSA_EXCEEDED_MEMORY_LIMIT; snprintf(r.message, sizeof(r.message), "the pair alone needs more resident memory than --memory-limit"); break;
-    case PAIR_ERR_TOO_LONG: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "template-switch column windows exceed 1056 columns at this cost threshold"); break;
+    case PAIR_ERR_TOO_LONG: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "offset / length hulls of the cost model exceed the 1056-column windows"); break;
     case PAIR_ERR_COST_RANGE: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "alignment cost exceeds the kernels' integer range (2^14 with template switches, else 2^26)"); break;
     case PAIR_ERR_LAYER_CAP: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "not proven optimal within max_template_switches template switches: refused"); break;
     case PAIR_ERR_FLANKS: r.status = TSA_ERR_UNSUPPORTED; snprintf(r.message, sizeof(r.message), "flank lengths above 255 are not supported"); break;
@@ -209,6 +209,7 @@ AlignOptions engine_options(const tsa_options& o) {
     a.scout_round = (o.reserved & 1) != 0;   // bit 0 of `reserved`: developer knob, enables the scouting round
     a.no_windows = (o.reserved & 2) != 0;    // bit 1: developer knob, medium pairs skip the column-window stage
     a.test_small_windows = (o.reserved & 4) != 0;   // bit 2: honoured by emulator builds only
+    a.test_tiled = (o.reserved & 8) != 0;           // bit 3: developer knob, pairs wider than 31 run only the tiled window stage
     if (o.reserved & 8) a.wave_checkpoints = 1;     // bit 3: developer knob, --no-ts alignments always through checkpoints (parity tests on short pairs)
     if (o.reserved & 16) a.wave_checkpoints = -1;   // bit 4: developer knob, --no-ts alignments always through the code matrix
     if (a.traceback) a.max_layers = std::min(a.max_layers, (int)MAX_TRACE_LAYERS);

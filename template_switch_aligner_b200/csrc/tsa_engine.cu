@@ -17,8 +17,9 @@ namespace {
 
 // Jump-kernel classes by pair width.  0..3: k_ts_jump<C, false> over the whole sequences (96 .. 544 columns).
 // 4 ("medium", up to 1055): column windows of 544 columns first (k_ts_jump<17, true>), whole sequences with C = 33 for
-// the pairs whose windows did not fit.  5 ("long", anything wider): windows of 544, then windows of 1056 columns; a pair
-// whose windows do not fit those either is refused (PAIR_ERR_TOO_LONG).
+// the pairs whose windows did not fit.  5 ("long", anything wider): windows of 544, then windows of 1056 columns, then (third
+// stage) 1056-column windows over sub-ranges of the entrance columns, which fit any pair; only a cost model whose offset /
+// length-difference hulls alone exceed the lane grid is refused (PAIR_ERR_TOO_LONG).
 constexpr int N_CLASS = 6;
 const int CLASS_C[N_CLASS] = {3, 5, 9, 17, 33, 33};
 
@@ -84,7 +85,7 @@ int jump_warps(int A, int C) {
 }
 
 template <int C, bool WIN>
-void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len, int A, int n_kinds, int ml, cudaStream_t stream, long long& launches) {
+void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len, int A, int n_kinds, int ml, cudaStream_t stream, long long& launches, int gz = 1) {
     ck.win_stage = stage;
     const int warps = jump_warps(A, C);
     const size_t smem = jump_smem_per_warp(A, C) * warps;
@@ -109,7 +110,7 @@ void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len
     for (int off = 0; off < n_list; off += 65535) {
         const int cnt = std::min(65535, n_list - off);
         auto kern = k_ts_jump<C, WIN>;
-        TSA_LAUNCH(kern, dim3(gx, (unsigned)cnt), dim3(32 * warps), smem, stream, ck, d_list + off, cnt);
+        TSA_LAUNCH(kern, dim3(gx, (unsigned)cnt, (unsigned)gz), dim3(32 * warps), smem, stream, ck, d_list + off, cnt);
         launches++;
     }
 }
@@ -299,6 +300,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
 #ifdef TSA_EMUL
             if (opt.test_small_windows && W > 48) cls = N_CLASS - 1;
 #endif
+            if (opt.test_tiled && W > 32) cls = N_CLASS - 1;
             I.class_list[cls].push_back((int)i);
             I.class_maxlen[cls] = std::max(I.class_maxlen[cls], W - 1);
             pm.lw = cls == N_CLASS - 1 ? (W + 7) & ~7 : 32 * CLASS_C[cls];
@@ -644,15 +646,26 @@ void Engine::run_staged() {
             jump_split(c, 2, l);
             break;
         default:  // long: windows of 544, then of 1056 columns
+            if (I.opt.test_tiled) {   // developer knob: only the tiled stage, with narrow sub-ranges
+#ifdef TSA_EMUL
+                launch_jump<5, true>(I.ck, 4, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, 2);
+#else
+                launch_jump<33, true>(I.ck, 4, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, 3);
+#endif
+                break;
+            }
 #ifdef TSA_EMUL
             if (I.opt.test_small_windows) {
                 launch_jump<3, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
                 launch_jump<5, true>(I.ck, 2, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+                launch_jump<5, true>(I.ck, 3, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, 2);
                 break;
             }
 #endif
             launch_jump<17, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
             launch_jump<33, true>(I.ck, 2, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            // third stage: the entrance columns of a chain pair in sub-ranges (any width; seeds combine through atomicMin)
+            launch_jump<33, true>(I.ck, 3, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, std::max(1, std::min(4, mx / 700)));
             break;
         }
         stats_.launches += l; stats_.jump_launches += l;
@@ -893,7 +906,7 @@ void Engine::run_trace() {
             case 4: launch_trace<33, false>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
             default:
 #ifdef TSA_EMUL
-                if (I.opt.test_small_windows) { launch_trace<5, true>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break; }
+                if (I.opt.test_small_windows || I.opt.test_tiled) { launch_trace<5, true>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break; }
 #endif
                 launch_trace<33, true>(I.ck, tl, to, I.rows, I.d_class_list[c], cnt, rows_max, dev_.A, I.stream, l); break;
             }
@@ -923,7 +936,7 @@ void Engine::fetch_staged(PairCost* out) {
         pc = PairCost();
         pc.status = I.status[i];
         if (pc.status != PAIR_OK) continue;
-        if (I.h_winflag[i] & 2) { pc.status = PAIR_ERR_TOO_LONG; continue; }   // a column window did not fit the widest class
+        if (I.h_winflag[i] & 4) { pc.status = PAIR_ERR_TOO_LONG; continue; }   // the hulls of the cost model alone exceed the widest lane grid
         if (!I.ts_enabled && h_sat[i] && I.h_best[i] >= WAVE_SAT) { pc.status = PAIR_ERR_COST_RANGE; continue; }   // exact only below 2^26 - 1
         if (I.ts_enabled && (I.h_active[i] || I.h_capped[i])) { pc.status = PAIR_ERR_LAYER_CAP; continue; }
         if (I.h_best[i] >= INF32) { pc.status = PAIR_NO_TARGET; continue; }

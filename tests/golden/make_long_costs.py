@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-CASES = [(600, 3, 2), (700, 4, 3), (900, 5, 3), (1100, 6, 3), (1300, 7, 4), (1600, 8, 4)]
+CASES = [(600, 3, 2), (700, 4, 3), (900, 5, 3), (1100, 6, 3), (1300, 7, 4), (1600, 8, 4), (2200, 9, 4), (3000, 41, 4)]
 OUT = os.path.join(HERE, "long_costs.json")
 
 

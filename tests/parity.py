@@ -110,7 +110,7 @@ def test_file_pairs(pairs, alphabet, max_len, min_len=0):
     return out
 
 
-def random_model_batches(lib, seeds, max_len, pairs_per_model=6, device=0, first_threshold=0, flanks=False):
+def random_model_batches(lib, seeds, max_len, pairs_per_model=6, device=0, first_threshold=0, flanks=False, dev_flags=0, min_len=0):
     """Random cost models (pieces, quirks, infinite entries) x random pairs and ranges."""
     total_ts = 0
     for seed in seeds:
@@ -120,8 +120,10 @@ def random_model_batches(lib, seeds, max_len, pairs_per_model=6, device=0, first
         ps = []
         for _ in range(pairs_per_model):
             r, q = randcfg.random_pair(rng, max_len=max_len)
+            while max(len(r), len(q)) < min_len:
+                r, q = randcfg.random_pair(rng, max_len=max_len)
             ps.append((r, q, randcfg.random_range(rng, r, q)))
         for no_ts in (False, True):
-            aligner = tsa.Aligner(costs=config_to_text(cfg), no_ts=no_ts, lib=lib, device=device, first_threshold=first_threshold or (1 + seed % 7))
+            aligner = tsa.Aligner(costs=config_to_text(cfg), no_ts=no_ts, lib=lib, device=device, first_threshold=first_threshold or (1 + seed % 7), dev_flags=dev_flags)
             total_ts += check_batch(aligner, flat, ps, no_ts=no_ts, label=f"seed {seed}")
     return total_ts

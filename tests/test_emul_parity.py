@@ -127,10 +127,33 @@ def test_column_windows_emulated():
         aligner = tsa.Aligner(costs=text, alphabet="dna-n", dev_flags=4, first_threshold=thr, lib=emul())
         total_ts += parity.check_batch(aligner, flat, pairs, label=f"windows {off}/{ld}/{lmax}")
     assert total_ts >= 3
-    # windows that do not fit the widest class are refused loudly, never answered wrongly
+    # a cost model whose offset / length-difference hulls alone exceed the lane grid (+-100 against the 160 columns of this
+    # build's widest windows) is refused loudly, never answered wrongly
     wide = tsa.Aligner(costs=base, alphabet="dna-n", dev_flags=4, lib=emul())
     res = wide.align_batch(workloads.read_pairs(1, start=500, length=200))[0]
     assert res.status == 9 and "windows" in res.message
+
+
+def test_tiled_windows_emulated():
+    # Third window stage: the entrance columns of a chain pair are cut into sub-ranges, each evaluated on its own windows, the
+    # seeds combined through atomicMin (no pair is refused for its width).  (1) dev_flags=8: every pair wider than 31 runs ONLY
+    # that stage with sub-ranges of at most 24 columns, under random cost models; (2) pairs whose bands overflow the 96- and the
+    # 160-column windows of this build and reach the stage the regular way.
+    from template_switch_aligner_b200 import workloads
+    from oracle import tsa_config
+    n_ts = parity.random_model_batches(emul(), range(0, 10), max_len=56, pairs_per_model=3, dev_flags=8, min_len=33)
+    assert n_ts >= 5
+    text = _narrow_model(workloads.sample_config_text(), 20, 5, 16)
+    flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+    pairs = []
+    for k in range(2):
+        r, q = workloads.long_pair(70 + k, 420, sub_rate=0.01, indel_rate=0.004, n_tsm=0)
+        for t in range(3):
+            p0 = 40 + 90 * t + 7 * k
+            q = q[:p0] + workloads.revcomp(r[p0 + 2:p0 + 2 + 12]) + q[p0 + 12:]
+        pairs.append((r, q))
+    aligner = tsa.Aligner(costs=text, alphabet="dna-n", dev_flags=4, lib=emul())
+    assert parity.check_batch(aligner, flat, pairs, label="tiled windows") == 2
 
 
 def test_flank_tiles_emulated():

@@ -262,23 +262,16 @@ def test_column_windows_gpu(lib):
         length, index, n_tsm = map(int, key.split("|"))
         cases.append(_long_case(length, index, n_tsm)); want.append(cost)
     assert len(cases) >= 4
-    # pairs of up to 1055 characters always get an answer (second stage = whole sequences); longer ones only when their
-    # windows fit 1056 columns, otherwise status 9.  Whatever is answered must be the oracle's optimum.
+    # every pair gets an answer: up to 1055 characters the second stage is the whole sequences; beyond, windows of 1056 columns
+    # and then the tiled stage (sub-ranges of the entrance columns).  The answer must be the oracle's optimum.
     got = win.align_batch(cases)
-    answered = 0
     for p, g, w in zip(cases, got, want):
-        if max(len(p[0]), len(p[1])) <= 1055:
-            assert g.status == 0, (len(p[0]), g.status, g.message)
-        else:
-            assert g.status in (0, 9), (len(p[0]), g.status, g.message)
-        if g.status == 0:
-            assert g.found and g.cost == w, (len(p[0]), g.cost, w)
-            parity.check_alignment(flat, p, g, "windows golden")
-            answered += 1
-    assert answered >= 3
+        assert g.status == 0, (len(p[0]), g.status, g.message)
+        assert g.found and g.cost == w, (len(p[0]), g.cost, w)
+        parity.check_alignment(flat, p, g, "windows golden")
     # long pairs beyond any whole-sequence class.  With the sample cost model a template switch may shift the diagonal by
     # +-100 columns for free, so the band of cheap cells grows with every layer: pairs whose optimum needs few switches
-    # fit the 1056-column windows; the others are refused loudly (status 9), never answered wrongly.
+    # fit the 1056-column windows, the others reach the tiled stage.
     easy = [workloads.long_pair(60 + k, 1500 + 900 * k, sub_rate=0.0005, indel_rate=0.0, n_tsm=1) for k in range(3)]
     res = win.align_batch(easy)
     nots = tsa.Aligner(costs=text, no_ts=True, lib=lib).align_batch(easy)
@@ -289,9 +282,34 @@ def test_column_windows_gpu(lib):
     assert sum(g.template_switches > 0 for g in res) >= 2
     hard = [_long_case(3000, 41, 4)]
     g = win.align_batch(hard)[0]
-    assert g.status in (0, 9)
-    if g.status == 0:
-        parity.check_alignment(flat, hard[0], g, "windows hard")
+    assert g.status == 0 and g.found, (g.status, g.message)
+    if "3000|41|4" in golden:
+        assert g.cost == golden["3000|41|4"]
+    parity.check_alignment(flat, hard[0], g, "windows hard")
+
+
+def test_tiled_windows_gpu(lib):
+    # The tiled window stage on its own (dev_flags=8: every pair wider than 31 runs only that stage, sub-ranges of at most 24
+    # entrance columns): random cost models against the oracle, the read pairs of config 2 against the completed A* costs, and
+    # a 4 kb pair with template switches (no pair is refused for its width; tools/time_long_ts.py runs 10 kb), rescored.
+    n_ts = parity.random_model_batches(lib, range(0, 40), max_len=64, pairs_per_model=6, dev_flags=8, min_len=33)
+    assert n_ts > 15
+    from conftest import load_golden
+    golden = load_golden("astar_c2.json")
+    text = workloads.sample_config_text()
+    flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
+    recs = [rec for rec in golden["pairs"] if rec["result"] == "FoundTarget"]
+    pairs = [workloads.read_pair(rec["index"], 150) for rec in recs]
+    got = tsa.Aligner(costs=text, dev_flags=8, lib=lib).align_batch(pairs)
+    for rec, p, g in zip(recs, pairs, got):
+        assert g.status == 0 and g.found and g.cost == rec["cost"], (rec["index"], g.cost, rec["cost"], g.message)
+        parity.check_alignment(flat, p, g, "tiled c2")
+    big = [workloads.long_pair(90, 4000, sub_rate=0.002, indel_rate=0.001, n_tsm=6)]
+    g = tsa.Aligner(costs=text, lib=lib).align_batch(big)[0]
+    h = tsa.Aligner(costs=text, no_ts=True, lib=lib).align_batch(big)[0]
+    assert g.status == 0 and g.found, (g.status, g.message)
+    assert g.cost < h.cost and g.template_switches >= 3
+    parity.check_alignment(flat, big[0], g, "4 kb with template switches")
 
 
 def test_single_long_pair_no_ts_gpu(lib):
