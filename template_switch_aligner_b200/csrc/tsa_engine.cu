@@ -289,7 +289,13 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         pm.seq_r = (long long)seq_bytes; seq_bytes += (size_t)pv.n;
         pm.seq_q = (long long)seq_bytes; seq_bytes += (size_t)pv.m;
         pm.vec = (long long)vec; vec += (size_t)pv.n + pv.m + 2;
-        pm.scr = (long long)scr; scr += (3 * ((size_t)pv.n + 1) + 1) & ~(size_t)1;   // even: k_affine_wave keeps 8-byte entries there
+        // even: k_affine_wave keeps 8-byte entries there; the multi-warp primary fill keeps one boundary column per warp
+#ifdef TSA_EMUL
+        const bool wide_fill = I.ts_enabled;     // (the emulator tests run the pipeline on 32-column blocks)
+#else
+        const bool wide_fill = I.ts_enabled && pv.m + 1 > 32 * K1_CB;
+#endif
+        pm.scr = (long long)scr; scr += ((3 * ((size_t)pv.n + 1) + 1) & ~(size_t)1) * (wide_fill ? K1_WIDE_MAX : 1);
         pm.mat = (long long)cells;
         pm.tab = -1; pm.lw = 0;
         const int W = std::max(pv.n, pv.m) + 1;
@@ -476,7 +482,16 @@ void Engine::run_staged() {
             I.ck.dir = I.dirL[layer]->as<uint8_t>();
             if (I.ts_enabled) { I.DL[layer]->ensure(I.cells * 2); I.ck.D = I.DL[layer]->as<int16_t>(); }
         }
+#ifdef TSA_EMUL
+        if ((I.opt.test_small_windows || I.opt.test_tiled) && I.ts_enabled && I.max_m + 1 > 32)   // CPU tests of the pipelined fill: 32-column blocks
+            TSA_LAUNCH((k_primary_fill<1, 4>), dim3((unsigned)cnt), dim3(32 * 4), (size_t)(4 * K1_SMEM_INTS + 1) * sizeof(int), I.stream, I.ck, d_list, cnt, layer);
+        else
+#endif
         if (I.max_m + 1 <= 32 * 5) TSA_LAUNCH(k_primary_fill<5>, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
+        else if (I.max_m + 1 > 32 * K1_CB * 4 && !I.opt.narrow_fill)   // several column blocks per pair: one CTA per pair, the blocks pipelined over its warps
+            TSA_LAUNCH((k_primary_fill<K1_CB, K1_WIDE_MAX>), dim3((unsigned)cnt), dim3(32 * K1_WIDE_MAX), (size_t)(K1_WIDE_MAX * K1_SMEM_INTS + 1) * sizeof(int), I.stream, I.ck, d_list, cnt, layer);
+        else if (I.max_m + 1 > 32 * K1_CB && !I.opt.narrow_fill)
+            TSA_LAUNCH((k_primary_fill<K1_CB, 4>), dim3((unsigned)cnt), dim3(32 * 4), (size_t)(4 * K1_SMEM_INTS + 1) * sizeof(int), I.stream, I.ck, d_list, cnt, layer);
         else TSA_LAUNCH(k_primary_fill<K1_CB>, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
         stats_.launches++; stats_.fill_launches++;
     };

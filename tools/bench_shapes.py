@@ -52,7 +52,7 @@ def measure(name, aligner, pairs, steps=3, extra=None):
     staged.close()
     bad = [r for r in res if not r.found]
     arr, keep = api._make_pairs(pairs)
-    opt = api._options(aligner.no_ts, aligner.device, None, None, traceback=aligner.traceback, postprocess=0)
+    opt = api._options(aligner.no_ts, aligner.device, None, None, traceback=aligner.traceback, postprocess=0, dev_flags=aligner.dev_flags)
     err = C.create_string_buffer(512)
     best = None
     for _ in range(steps):
@@ -79,10 +79,11 @@ def measure(name, aligner, pairs, steps=3, extra=None):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    args = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()]
     shapes = args or ["c4", "c5", "c3"]
     n_pairs = int(sys.argv[sys.argv.index("--pairs") + 1]) if "--pairs" in sys.argv else None
     text = workloads.sample_config_text()
+    dev_flags = int(sys.argv[sys.argv.index("--dev-flags") + 1]) if "--dev-flags" in sys.argv else 0   # 16: one warp per pair in the primary fill
     if "c4" in shapes:
         pairs = [workloads.long_pair(i, 10000) for i in range(n_pairs or 1024)]
         for tb in (False, True):
@@ -95,7 +96,7 @@ def main():
         fl = 50
         ftext = text.replace("left_flank_length = 0", f"left_flank_length = {fl}").replace("right_flank_length = 0", f"right_flank_length = {fl}")
         pairs = [workloads.long_pair(i, 1000, indel_rate=0.0, n_tsm=5) for i in range(n_pairs or 16)]
-        measure("c3: 1 kb pairs, 5 planted TSMs, flanks 50/50", tsa.Aligner(costs=ftext), pairs, steps=2)
+        measure("c3: 1 kb pairs, 5 planted TSMs, flanks 50/50", tsa.Aligner(costs=ftext, dev_flags=dev_flags), pairs, steps=2, extra={"dev_flags": dev_flags})
     return 0
 
 
