@@ -117,7 +117,7 @@ void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len
 
 // Pairs without column windows: row kernel -> row queue -> evaluation kernel, in slices of pairs whose candidate rows fit the queue.
 // counts[slice] receives the slots each slice asked for (the caller compares them with the capacity after the layer).
-template <int C>
+template <int C, bool WIN = false>
 void launch_jump_split(Chunk ck, int stage, const int* d_list, int n_list, int max_len, int A, int n_kinds, int ml, cudaStream_t stream, long long& launches,
                        int slice_pairs, int* d_counts, int& n_slices, std::vector<int>& slice_size) {
     ck.win_stage = stage;
@@ -130,8 +130,8 @@ void launch_jump_split(Chunk ck, int stage, const int* d_list, int n_list, int m
     int dev = 0;
     cudaGetDevice(&dev);
     if (once.first()) {
-        auto row = k_ts_jump<C, false, true>;
-        auto eval = k_ts_eval<C>;
+        auto row = k_ts_jump<C, WIN, true>;
+        auto eval = k_ts_eval<C, WIN>;
         rt::check(cudaFuncSetAttribute(row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
         rt::check(cudaFuncSetAttribute(row, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
         rt::check(cudaFuncSetAttribute(eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
@@ -146,7 +146,7 @@ void launch_jump_split(Chunk ck, int stage, const int* d_list, int n_list, int m
             cudaFuncGetAttributes(&fa, row); cudaFuncGetAttributes(&fb, eval);
             int row_blocks = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_blocks, row, 32 * warps, smem_row);
-            fprintf(stderr, "[tsalign_b200] C=%d: row kernel %d regs, %d blocks/SM; eval kernel %d regs, %d blocks/SM\n", C, fa.numRegs, row_blocks, fb.numRegs, per_sm);
+            fprintf(stderr, "[tsalign_b200] C=%d windows=%d: row kernel %d regs, %d blocks/SM; eval kernel %d regs, %d blocks/SM\n", C, (int)WIN, fa.numRegs, row_blocks, fb.numRegs, per_sm);
         }
     }
     eval_blocks = resident[dev & 63];
@@ -162,8 +162,8 @@ void launch_jump_split(Chunk ck, int stage, const int* d_list, int n_list, int m
         ck.q_count = d_counts + n_slices;
         slice_size.push_back(cnt);
         n_slices++;
-        auto row = k_ts_jump<C, false, true>;
-        auto eval = k_ts_eval<C>;
+        auto row = k_ts_jump<C, WIN, true>;
+        auto eval = k_ts_eval<C, WIN>;
         TSA_LAUNCH(row, dim3(gx, (unsigned)cnt), dim3(32 * warps), smem_row, stream, ck, d_list + off, cnt);
         TSA_LAUNCH(eval, dim3((unsigned)eval_blocks), dim3(32 * warps), smem_eval, stream, ck);
         launches += 2;
@@ -604,21 +604,23 @@ void Engine::run_staged() {
     // Row queue of the split jump (classes without column windows): sized from the learned demand per pair, at least the worst case
     // of one pair (every row of every chain queued), at most 6 GiB.
     int n_slices = 0, est_r = 0, est_l = 0;      // bucket of the learned demand the current layer uses
-    std::vector<int> slice_size, slice_class, h_qcounts;
+    std::vector<int> slice_size, slice_class, slice_lw, h_qcounts;
     auto est = [&](int c) -> double& { return I.q_est[c][est_r][est_l]; };
     {
         size_t want = 0, one = 0;
         int min_lw = 1 << 30;
-        for (int c = 0; c < N_CLASS - 1; c++) {
+        for (int c = 0; c < N_CLASS; c++) {
             if (I.class_list[c].empty()) continue;
-            const int LW = 32 * CLASS_C[c], mx = I.class_maxlen[c];
+            // (the first window stage of the medium and long classes queues 544-column rows; long pairs only use the queue there)
+            const int LW = c == N_CLASS - 1 ? 32 * 17 : 32 * CLASS_C[c], mx = I.class_maxlen[c];
             const int n_ep = std::max(0, (mx - dev_.ml + 2) / 2);
             const double chains = (double)dev_.n_kinds * n_ep;
             const double rows_max = (double)std::min(dev_.lmax, mx) + 1 + QUEUE_RESERVE;
             for (auto& byround : I.q_est[c]) for (double& v : byround) if (v <= 0) v = chains * 2.0;
-            one = std::max(one, (size_t)(chains * rows_max) * LW * 4);
+            // a long pair whose candidate rows do not fit falls back to the fused windowed kernel (jump_layer)
+            one = std::max(one, c == N_CLASS - 1 ? std::min((size_t)(chains * rows_max) * LW * 4, (size_t)2 << 30) : (size_t)(chains * rows_max) * LW * 4);
             want += (size_t)((double)I.class_list[c].size() * I.q_est[c][0][0] * 1.3) * LW * 4;
-            min_lw = std::min(min_lw, LW);
+            min_lw = std::min(min_lw, c >= 4 ? 32 * 17 : LW);
         }
         if (min_lw < (1 << 30)) {
             size_t cap_bytes = (size_t)16 << 30;      // fewer, larger slices are faster (measured: 6 / 12 / 24 GiB)
@@ -632,24 +634,37 @@ void Engine::run_staged() {
             I.q_counts.ensure((size_t)MAX_Q_SLICES * 4);
         }
     }
-    auto jump_split = [&](int c, int stage, long long& l) {
+    // cw: columns per lane of the instantiation (0: the class's own); win: the windowed kernels (k_ts_jump<C, true, true> / k_ts_eval<C, true>)
+    auto jump_split = [&](int c, int stage, long long& l, int cw = 0, bool win = false) {
         Chunk ck = I.ck;
-        const int LW = 32 * CLASS_C[c];
+        const int CW = cw ? cw : CLASS_C[c];
+        const int LW = 32 * CW;
         ck.q_cap = (int)std::min<size_t>(I.q_rows.cap / ((size_t)LW * 4), (size_t)1 << 30) & ~(QUEUE_RESERVE - 1);   // whole reservation blocks
         ck.q_hdr = I.q_hdr.as<QueueHdr>();
         ck.q_rows = I.q_rows.as<uint32_t>();
         const int slice_pairs = (int)std::max(1.0, std::min(65535.0, (double)ck.q_cap / (est(c) * 1.3)));
         const int ml_ = dev_.ml, A_ = dev_.A, nk = dev_.n_kinds, mx = I.class_maxlen[c];
         int* counts = I.q_counts.as<int>();
-        switch (c) {
-        case 0: launch_jump_split<3>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
-        case 1: launch_jump_split<5>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
-        case 2: launch_jump_split<9>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
-        case 3: launch_jump_split<17>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+        if (win) {
+            switch (CW) {
+#ifdef TSA_EMUL
+            case 3: launch_jump_split<3, true>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+#endif
+            case 17: launch_jump_split<17, true>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+            default: throw std::runtime_error("no windowed split jump of this width");
+            }
+        } else
+        switch (CW) {
+        case 3: launch_jump_split<3>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+        case 5: launch_jump_split<5>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+        case 9: launch_jump_split<9>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
+        case 17: launch_jump_split<17>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
         default: launch_jump_split<33>(ck, stage, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, slice_pairs, counts, n_slices, slice_size); break;
         }
         slice_class.resize(slice_size.size(), c);
+        slice_lw.resize(slice_size.size(), LW);
     };
+    bool force_fused[N_CLASS] = {false};      // the candidate rows of ONE pair of the class overflowed the queue: fused windowed kernel from then on
     auto jump_class = [&](int c) {
         long long l = 0;
         const int ml_ = dev_.ml, A_ = dev_.A, nk = dev_.n_kinds, mx = I.class_maxlen[c];
@@ -657,7 +672,8 @@ void Engine::run_staged() {
         case 0: case 1: case 2: case 3: jump_split(c, 0, l); break;
         case 4:   // medium: windows of 544 columns, then the whole sequences for the pairs that were flagged
             if (I.opt.no_windows) { jump_split(c, 0, l); break; }
-            launch_jump<17, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            if (I.opt.fused_windows || force_fused[c]) launch_jump<17, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            else jump_split(c, 1, l, 17, true);
             jump_split(c, 2, l);
             break;
         default:  // long: windows of 544, then of 1056 columns
@@ -671,13 +687,15 @@ void Engine::run_staged() {
             }
 #ifdef TSA_EMUL
             if (I.opt.test_small_windows) {
-                launch_jump<3, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+                if (I.opt.fused_windows) launch_jump<3, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+                else jump_split(c, 1, l, 3, true);
                 launch_jump<5, true>(I.ck, 2, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
                 launch_jump<5, true>(I.ck, 3, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, 2);
                 break;
             }
 #endif
-            launch_jump<17, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            if (I.opt.fused_windows || force_fused[c]) launch_jump<17, true>(I.ck, 1, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
+            else jump_split(c, 1, l, 17, true);
             launch_jump<33, true>(I.ck, 2, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l);
             // third stage: the entrance columns of a chain pair in sub-ranges (any width; seeds combine through atomicMin)
             launch_jump<33, true>(I.ck, 3, cur[c], cur_n[c], mx, A_, nk, ml_, I.stream, l, std::max(1, std::min(4, mx / 700)));
@@ -689,7 +707,7 @@ void Engine::run_staged() {
     // updated from the exact count and the jump of the layer is repeated with smaller slices (seeds are minima: repeating is exact).
     auto jump_layer = [&]() {
         for (int attempt = 0;; attempt++) {
-            n_slices = 0; slice_size.clear(); slice_class.clear();
+            n_slices = 0; slice_size.clear(); slice_class.clear(); slice_lw.clear();
             if (I.q_counts.p) rt::dev_memset(I.q_counts.p, 0, (size_t)MAX_Q_SLICES * 4, I.stream);
             mark(2);
             for (int c = 0; c < N_CLASS; c++) if (cur_n[c]) jump_class(c);
@@ -701,11 +719,12 @@ void Engine::run_staged() {
             bool overflow = false;
             for (int s2 = 0; s2 < n_slices; s2++) {
                 const int c = slice_class[(size_t)s2];
-                const size_t cap = std::min<size_t>(I.q_rows.cap / ((size_t)32 * CLASS_C[c] * 4), (size_t)1 << 30);
+                const size_t cap = std::min<size_t>(I.q_rows.cap / ((size_t)slice_lw[(size_t)s2] * 4), (size_t)1 << 30);
                 est(c) = std::max(est(c), (double)h_qcounts[(size_t)s2] / std::max(1, slice_size[(size_t)s2]));
                 if ((size_t)h_qcounts[(size_t)s2] > cap) {
                     overflow = true;
-                    if (slice_size[(size_t)s2] == 1 || attempt > 8) throw std::runtime_error("row queue: one pair does not fit the queue");
+                    if (slice_size[(size_t)s2] == 1 && slice_lw[(size_t)s2] < 32 * CLASS_C[c] && !force_fused[c]) force_fused[c] = true;
+                    else if (slice_size[(size_t)s2] == 1 || attempt > 8) throw std::runtime_error("row queue: one pair does not fit the queue");
                 }
             }
             if (getenv("TSA_B200_DEBUG")) fprintf(stderr, "[tsalign_b200] jump layer: attempt %d, %d slices, overflow %d, q_est %.0f\n", attempt, n_slices, (int)overflow, est(1));

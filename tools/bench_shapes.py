@@ -92,6 +92,10 @@ def main():
         pair = c5_pair()
         for tb in (False, True):
             measure(f"c5 shape: one {len(pair[0])} x {len(pair[1])} pair, --no-ts, alignment={tb}, one GPU", tsa.Aligner(costs=text, no_ts=True, traceback=tb), [pair])
+    if "medium" in shapes:
+        # pairs of the "medium" jump class (545 .. 1055 characters): column windows of 544 columns, template switches on, no flanks
+        pairs = [workloads.long_pair(200 + i, 800, sub_rate=0.004, indel_rate=0.002, n_tsm=3) for i in range(n_pairs or 256)]
+        measure("medium: 800 bp pairs, 3 planted TSMs, sample config", tsa.Aligner(costs=text, dev_flags=dev_flags), pairs, steps=2, extra={"dev_flags": dev_flags})
     if "c3" in shapes:
         fl = 50
         ftext = text.replace("left_flank_length = 0", f"left_flank_length = {fl}").replace("right_flank_length = 0", f"right_flank_length = {fl}")
