@@ -389,6 +389,26 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     auto t1 = std::chrono::steady_clock::now();
     std::vector<PairCost> costs(enc.views.size());
     const size_t live = enc.views.size();
+    for (size_t i = 0; i < n; i++) {
+        memset(&out[i], 0, sizeof(tsa_result));
+        out[i].status = enc.pair_status[i];
+        snprintf(out[i].message, sizeof(out[i].message), "%s", enc.pair_msg[i].c_str());
+    }
+    // result assembly + post-processing of the pairs [lo, hi) of the encoded list (host cores)
+    std::vector<char> done(enc.live.size(), 0);
+    auto finish = [&](size_t lo, size_t hi) {
+        parallel_for(hi - lo, [&](size_t t) {
+            const size_t k = lo + t;
+            if (done[k]) return;
+            tsa_result& r = out[enc.live[k]];
+            fill_result(r, costs[k], o);
+            const PairView& pv = enc.views[k];
+            r.reference_offset = pv.ro; r.reference_limit = pv.rl; r.query_offset = pv.qo; r.query_limit = pv.ql;
+            postprocess_result(cfg->host, pv, o.postprocess, r);
+            done[k] = 1;
+        });
+    };
+    const bool pipelined = o.descendant_strategy != 1;      // (the better of two searches is only known after both)
     auto run_engines = [&](const AlignOptions& ao, std::vector<PairCost>& costs) -> int {
 #ifndef TSA_EMUL
     const bool split = live >= 4096 && !o.no_ts;
@@ -401,13 +421,24 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
         if (!mcfg->engine2[slot] || !mcfg->engine2[slot]->ok()) mcfg->engine2[slot].reset(new Engine(cfg->host, o.device));
         Engine& second = *mcfg->engine2[slot];
         if (!second.ok()) { set_err(err, errcap, second.error()); mcfg->engine2[slot].reset(); return TSA_ERR_NO_DEVICE; }
+        // Each half in `parts` pieces: the results of a piece are assembled and post-processed on the host cores right after its
+        // kernels, while the kernels of the other engine keep the GPU busy.
         const size_t half = live / 2;
-                std::exception_ptr failed;
+        static const size_t parts_env = []() -> size_t { const char* e = getenv("TSA_B200_PARTS"); const long v = e ? atol(e) : 0; return v > 0 ? (size_t)v : 1; }();   // measured on B200 (16 384 read pairs): 1 / 2 / 4 pieces per half -> 2.05 / 2.00 / 1.84 GCUPS end to end
+        const size_t parts = pipelined ? std::max<size_t>(1, std::min(parts_env, half / 2048)) : 1;
+        auto run_half = [&](Engine& eng, size_t lo, size_t hi) {
+            for (size_t p = 0; p < parts; p++) {
+                const size_t a = lo + (hi - lo) * p / parts, b2 = lo + (hi - lo) * (p + 1) / parts;
+                eng.align_costs(enc.views.data() + a, b2 - a, ao, costs.data() + a);
+                if (pipelined) finish(a, b2);
+            }
+        };
+        std::exception_ptr failed;
         std::thread other([&]() {
-            try { second.align_costs(enc.views.data() + half, live - half, ao, costs.data() + half); }
+            try { run_half(second, half, live); }
             catch (...) { failed = std::current_exception(); }
         });
-        try { engine.align_costs(enc.views.data(), half, ao, costs.data()); }
+        try { run_half(engine, 0, half); }
         catch (...) { other.join(); throw; }
         other.join();
         if (failed) std::rethrow_exception(failed);
@@ -440,15 +471,9 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
         if (rc1 != TSA_OK) return rc1;
     }
     auto t2 = std::chrono::steady_clock::now();
-    for (size_t i = 0; i < n; i++) {
-        memset(&out[i], 0, sizeof(tsa_result));
-        out[i].status = enc.pair_status[i];
-        snprintf(out[i].message, sizeof(out[i].message), "%s", enc.pair_msg[i].c_str());
-    }
     // --memory-limit without template switches: a pair whose code matrix does not fit is aligned by the checkpointed path of
     // tsa_long.cu (checkpoint rows + recomputed tiles under the same limit): the limit bounds what is resident, the alignment is
     // still produced; ExceededMemoryLimit only if not even the checkpoints fit.
-    std::vector<char> done(enc.live.size(), 0);
     if (o.no_ts) for (size_t k = 0; k < enc.live.size(); k++) if (costs[k].status == PAIR_MEMORY_LIMIT) {
         const PairView& pv = enc.views[k];
         tsa_result& r = out[enc.live[k]];
@@ -464,14 +489,7 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
         }
         done[k] = 1;
     }
-    parallel_for(enc.live.size(), [&](size_t k) {
-        if (done[k]) return;
-        tsa_result& r = out[enc.live[k]];
-        fill_result(r, costs[k], o);
-        const PairView& pv = enc.views[k];
-        r.reference_offset = pv.ro; r.reference_limit = pv.rl; r.query_offset = pv.qo; r.query_limit = pv.ql;
-        postprocess_result(cfg->host, pv, o.postprocess, r);
-    });
+    finish(0, enc.live.size());
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (getenv("TSA_B200_DEBUG"))
         fprintf(stderr, "[tsalign_b200] align_batch n=%zu: encode %.2f ms, engine %.2f ms, results %.2f ms\n", n,
