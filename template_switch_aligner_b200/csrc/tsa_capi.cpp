@@ -46,6 +46,24 @@ struct Encoded {
 };
 
 // tsalign/src/align.rs:389-405 (VectorGenome::from_slice_u8) + AlignmentRange checks.
+// Result assembly (run-length encoding, post-processing) of a batch on the host cores.
+template <class F>
+void parallel_for(size_t n, F&& body) {
+    // host threads of this process: TSA_B200_THREADS, else the cores divided among the ranks of a torchrun launch
+    static const size_t hw = []() -> size_t {
+        size_t cores = std::max<size_t>(1, std::thread::hardware_concurrency());
+        if (const char* t = getenv("TSA_B200_THREADS")) { const long v = atol(t); if (v > 0) return (size_t)v; }
+        if (const char* w = getenv("LOCAL_WORLD_SIZE")) { const long v = atol(w); if (v > 1) cores = std::max<size_t>(1, cores / (size_t)v); }
+        return cores;
+    }();
+    const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), (n + 255) / 256);
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) body(i); return; }
+    std::vector<std::thread> th;
+    std::atomic<size_t> next(0);
+    for (size_t t = 0; t < nt; t++) th.emplace_back([&]() { for (;;) { const size_t lo = next.fetch_add(64); if (lo >= n) break; for (size_t i = lo; i < std::min(n, lo + 64); i++) body(i); } });
+    for (auto& x : th) x.join();
+}
+
 void encode_pairs(const HostConfig& cfg, const tsa_pair* pairs, size_t n, Encoded& e) {
     int lut[256];
     for (int c = 0; c < 256; c++) lut[c] = alphabet_index(cfg.alphabet, (unsigned char)c);
@@ -54,10 +72,12 @@ void encode_pairs(const HostConfig& cfg, const tsa_pair* pairs, size_t n, Encode
     e.pool.resize(total + 1);
     e.pair_status.assign(n, TSA_OK);
     e.pair_msg.assign(n, std::string());
-    size_t off = 0;
+    std::vector<size_t> offs(n + 1, 0);
+    for (size_t i = 0; i < n; i++) offs[i + 1] = offs[i] + pairs[i].reference_len + pairs[i].query_len;
     std::vector<PairView> all(n);
-    for (size_t i = 0; i < n; i++) {
+    parallel_for(n, [&](size_t i) {   // (every pair writes its own slice of the pool and its own status / message)
         const tsa_pair& p = pairs[i];
+        size_t off = offs[i];
         PairView v;
         v.ref = &e.pool[off];
         for (size_t k = 0; k < p.reference_len; k++) {
@@ -81,7 +101,7 @@ void encode_pairs(const HostConfig& cfg, const tsa_pair* pairs, size_t n, Encode
         if (e.pair_status[i] == TSA_OK && (p.reference_len > (size_t)1 << 30 || p.query_len > (size_t)1 << 30)) { e.pair_status[i] = TSA_ERR_UNSUPPORTED; e.pair_msg[i] = "sequence too long"; }
         v.ro = (int)p.reference_offset; v.rl = (int)rl; v.qo = (int)p.query_offset; v.ql = (int)ql;
         all[i] = v;
-    }
+    });
     for (size_t i = 0; i < n; i++) if (e.pair_status[i] == TSA_OK) { e.live.push_back(i); e.views.push_back(all[i]); }
 }
 
@@ -180,24 +200,6 @@ void postprocess_result(const HostConfig& cfg, const PairView& pv, int32_t flags
     if (ops.size() != r.n_ops) { free(r.ops); r.ops = (tsa_op*)malloc(sizeof(tsa_op) * std::max<size_t>(1, ops.size())); r.n_ops = ops.size(); }
     from_post(ops, r.ops);
     r.reference_offset = ro; r.reference_limit = rl; r.query_offset = qo; r.query_limit = ql;
-}
-
-// Result assembly (run-length encoding, post-processing) of a batch on the host cores.
-template <class F>
-void parallel_for(size_t n, F&& body) {
-    // host threads of this process: TSA_B200_THREADS, else the cores divided among the ranks of a torchrun launch
-    static const size_t hw = []() -> size_t {
-        size_t cores = std::max<size_t>(1, std::thread::hardware_concurrency());
-        if (const char* t = getenv("TSA_B200_THREADS")) { const long v = atol(t); if (v > 0) return (size_t)v; }
-        if (const char* w = getenv("LOCAL_WORLD_SIZE")) { const long v = atol(w); if (v > 1) cores = std::max<size_t>(1, cores / (size_t)v); }
-        return cores;
-    }();
-    const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), (n + 255) / 256);
-    if (nt <= 1) { for (size_t i = 0; i < n; i++) body(i); return; }
-    std::vector<std::thread> th;
-    std::atomic<size_t> next(0);
-    for (size_t t = 0; t < nt; t++) th.emplace_back([&]() { for (;;) { const size_t lo = next.fetch_add(64); if (lo >= n) break; for (size_t i = lo; i < std::min(n, lo + 64); i++) body(i); } });
-    for (auto& x : th) x.join();
 }
 
 AlignOptions engine_options(const tsa_options& o) {
