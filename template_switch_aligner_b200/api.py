@@ -339,7 +339,7 @@ class Aligner:
         self.descendant_strategy = descendant_strategy
         self.force_label_correcting = bool(force_label_correcting)
         self.max_template_switches = int(max_template_switches)
-        self.dev_flags = int(dev_flags)         # developer knobs (2: no column windows for medium pairs; 4: small windows, emulator only; 8: pairs wider than 31 through the tiled window stage only; 16: one warp per pair in the primary fill)
+        self.dev_flags = int(dev_flags)         # developer knobs (2: no column windows for medium pairs; 4: small windows, emulator only; 8 / 16: --no-ts alignments always through checkpoints / the code matrix; 32: first window stage fused; 64: pairs wider than 31 through the tiled window stage only; 128: one warp per pair in the primary fill)
         self.first_threshold = first_threshold  # tuning of the exact pruning only; results do not depend on it
         self.config = Config(costs, alphabet, lib=self._lib)
 

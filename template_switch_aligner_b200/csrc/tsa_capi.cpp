@@ -212,8 +212,8 @@ AlignOptions engine_options(const tsa_options& o) {
     a.no_windows = (o.reserved & 2) != 0;    // bit 1: developer knob, medium pairs skip the column-window stage
     a.test_small_windows = (o.reserved & 4) != 0;   // bit 2: honoured by emulator builds only
     a.fused_windows = (o.reserved & 32) != 0;       // bit 5: developer knob, first window stage through the fused jump kernel
-    a.narrow_fill = (o.reserved & 16) != 0;         // bit 4: developer knob, one warp per pair in the primary fill whatever the length
-    a.test_tiled = (o.reserved & 8) != 0;           // bit 3: developer knob, pairs wider than 31 run only the tiled window stage
+    a.narrow_fill = (o.reserved & 128) != 0;        // bit 7: developer knob, one warp per pair in the primary fill whatever the length
+    a.test_tiled = (o.reserved & 64) != 0;          // bit 6: developer knob, pairs wider than 31 run only the tiled window stage
     if (o.reserved & 8) a.wave_checkpoints = 1;     // bit 3: developer knob, --no-ts alignments always through checkpoints (parity tests on short pairs)
     if (o.reserved & 16) a.wave_checkpoints = -1;   // bit 4: developer knob, --no-ts alignments always through the code matrix
     if (a.traceback) a.max_layers = std::min(a.max_layers, (int)MAX_TRACE_LAYERS);

@@ -1028,14 +1028,35 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
         budget = (size_t)1 << 30;
 #endif
     }
+    // --no-ts with alignments: long pairs keep checkpoint rows + boundary columns instead of a code matrix (stage() decides the same
+    // way per chunk; the decision of the whole job is handed down so that every chunk is sized for what it will allocate)
+    bool job_ck = false;
+    if ((opt.no_ts || dev_.n_kinds == 0) && opt.traceback && n > 0 && opt.wave_checkpoints >= 0) {
+        double range_cells = 0;
+        for (size_t k = 0; k < n; k++) range_cells += (double)(pairs[k].rl - pairs[k].ro + 1) * (double)(pairs[k].ql - pairs[k].qo + 1);
+        job_ck = opt.wave_checkpoints > 0 || range_cells / (double)n >= (double)(1 << 22);
+    }
     auto resident_bytes = [&](const PairView& p) {
         const size_t cells = (size_t)(p.n + 1) * (p.m + 1);
         size_t b = (!opt.no_ts && dev_.n_kinds > 0) ? bytes_per_pair(p.n, p.m) : (size_t)(p.n + p.m) * 20 + 512;
+        if (job_ck) {
+            const size_t nn = (size_t)(p.rl - p.ro), mm = (size_t)(p.ql - p.qo);
+            return b + std::max<size_t>(1, nn / BB_INTERVAL) * (mm + 2) * 12 + (size_t)((wave_strips((int)mm + 1) + BB_GROUP - 1) / BB_GROUP) * (nn + 1) * 8
+                     + 3 * (size_t)(p.n + p.m) + 256;
+        }
         if (opt.traceback) b += cells * ((!opt.no_ts && dev_.n_kinds > 0) ? 9 : 1) + 3 * (size_t)(p.n + p.m) + 256;   // codes (+ D) of ~3 layers, ops
         if (!opt.no_ts && dev_.n_kinds > 0 && (dev_.left_flank > 0 || dev_.right_flank > 0))   // flank planes, and their codes of ~4 layers
             b += cells * (12 + (opt.traceback ? (size_t)(dev_.left_flank + dev_.right_flank + 1) * 4 : 0));
         return b;
     };
+    // chunks of about equal size: as few as the budget allows, none much smaller than the others (a small last chunk runs at
+    // a fraction of the throughput of a full one)
+    size_t target = budget;
+    {
+        size_t all = 0;
+        for (size_t k = 0; k < n; k++) all += resident_bytes(pairs[k]);
+        if (all > budget) target = all / ((all + budget - 1) / budget) + 1;
+    }
     while (i < n) {
         if (opt.memory_limit_strict && resident_bytes(pairs[i]) > budget) {
             // generic_a_star/src/lib.rs:380-389: the search gives up when its store outgrows the limit.  (The C ABI re-runs pairs
@@ -1049,9 +1070,11 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
             const size_t b = resident_bytes(pairs[j]);
             if (j > i && bytes + b > budget) break;
             bytes += b; j++;
+            if (bytes >= target) break;
         }
         const auto cs = std::chrono::steady_clock::now();
         AlignOptions o = opt;
+        if (job_ck) o.wave_checkpoints = std::max(o.wave_checkpoints, 1);
         o.chunk_bytes = (size_t)1 << 62;   // the chunk was sized above; stage() must not refuse it
         if (!stage(pairs + i, j - i, o)) {
             for (size_t k = i; k < j; k++) { out[k] = PairCost(); out[k].status = PAIR_ERR_TOO_LONG; }

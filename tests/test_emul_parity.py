@@ -136,12 +136,12 @@ def test_column_windows_emulated():
 
 def test_tiled_windows_emulated():
     # Third window stage: the entrance columns of a chain pair are cut into sub-ranges, each evaluated on its own windows, the
-    # seeds combined through atomicMin (no pair is refused for its width).  (1) dev_flags=8: every pair wider than 31 runs ONLY
+    # seeds combined through atomicMin (no pair is refused for its width).  (1) dev_flags=64: every pair wider than 31 runs ONLY
     # that stage with sub-ranges of at most 24 columns, under random cost models; (2) pairs whose bands overflow the 96- and the
     # 160-column windows of this build and reach the stage the regular way.
     from template_switch_aligner_b200 import workloads
     from oracle import tsa_config
-    n_ts = parity.random_model_batches(emul(), range(0, 7), max_len=56, pairs_per_model=3, dev_flags=8, min_len=33)
+    n_ts = parity.random_model_batches(emul(), range(0, 7), max_len=56, pairs_per_model=3, dev_flags=64, min_len=33)
     assert n_ts >= 3
     text = _narrow_model(workloads.sample_config_text(), 20, 5, 16)
     flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
@@ -158,7 +158,7 @@ def test_tiled_windows_emulated():
     # more blocks than warps) and the tiled stage
     r, q = workloads.read_pair(77, 150)
     ragged = [(r[:5], q), (r, q[:5]), ("", q[:40]), (r[:40], ""), (r[:33], q[:33]), (r[:16], q[:140]), (r[:140], q[:17])]
-    aligner = tsa.Aligner(costs=text, alphabet="dna-n", dev_flags=8, lib=emul())
+    aligner = tsa.Aligner(costs=text, alphabet="dna-n", dev_flags=64, lib=emul())
     parity.check_batch(aligner, flat, ragged, label="ragged")
 
 

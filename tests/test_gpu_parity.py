@@ -289,10 +289,10 @@ def test_column_windows_gpu(lib):
 
 
 def test_tiled_windows_gpu(lib):
-    # The tiled window stage on its own (dev_flags=8: every pair wider than 31 runs only that stage, sub-ranges of at most 24
+    # The tiled window stage on its own (dev_flags=64: every pair wider than 31 runs only that stage, sub-ranges of at most 24
     # entrance columns): random cost models against the oracle, the read pairs of config 2 against the completed A* costs, and
     # a 4 kb pair with template switches (no pair is refused for its width; tools/time_long_ts.py runs 10 kb), rescored.
-    n_ts = parity.random_model_batches(lib, range(0, 40), max_len=64, pairs_per_model=6, dev_flags=8, min_len=33)
+    n_ts = parity.random_model_batches(lib, range(0, 40), max_len=64, pairs_per_model=6, dev_flags=64, min_len=33)
     assert n_ts > 15
     from conftest import load_golden
     golden = load_golden("astar_c2.json")
@@ -300,7 +300,7 @@ def test_tiled_windows_gpu(lib):
     flat = oracle.FlatConfig(tsa_config.parse(text, "dna-n"))
     recs = [rec for rec in golden["pairs"] if rec["result"] == "FoundTarget"]
     pairs = [workloads.read_pair(rec["index"], 150) for rec in recs]
-    got = tsa.Aligner(costs=text, dev_flags=8, lib=lib).align_batch(pairs)
+    got = tsa.Aligner(costs=text, dev_flags=64, lib=lib).align_batch(pairs)
     for rec, p, g in zip(recs, pairs, got):
         assert g.status == 0 and g.found and g.cost == rec["cost"], (rec["index"], g.cost, rec["cost"], g.message)
         parity.check_alignment(flat, p, g, "tiled c2")
