@@ -48,7 +48,7 @@ struct Encoded {
 // tsalign/src/align.rs:389-405 (VectorGenome::from_slice_u8) + AlignmentRange checks.
 // Result assembly (run-length encoding, post-processing) of a batch on the host cores.
 template <class F>
-void parallel_for(size_t n, F&& body) {
+void parallel_for(size_t n, F&& body, size_t threads_hint = 0) {
     // host threads of this process: TSA_B200_THREADS, else the cores divided among the ranks of a torchrun launch
     static const size_t hw = []() -> size_t {
         size_t cores = std::max<size_t>(1, std::thread::hardware_concurrency());
@@ -56,7 +56,7 @@ void parallel_for(size_t n, F&& body) {
         if (const char* w = getenv("LOCAL_WORLD_SIZE")) { const long v = atol(w); if (v > 1) cores = std::max<size_t>(1, cores / (size_t)v); }
         return cores;
     }();
-    const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), (n + 255) / 256);
+    const size_t nt = std::min<size_t>(std::min<size_t>(hw, 32), std::max((n + 255) / 256, std::min(threads_hint, (n + 63) / 64)));
     if (nt <= 1) { for (size_t i = 0; i < n; i++) body(i); return; }
     std::vector<std::thread> th;
     std::atomic<size_t> next(0);
@@ -101,7 +101,7 @@ void encode_pairs(const HostConfig& cfg, const tsa_pair* pairs, size_t n, Encode
         if (e.pair_status[i] == TSA_OK && (p.reference_len > (size_t)1 << 30 || p.query_len > (size_t)1 << 30)) { e.pair_status[i] = TSA_ERR_UNSUPPORTED; e.pair_msg[i] = "sequence too long"; }
         v.ro = (int)p.reference_offset; v.rl = (int)rl; v.qo = (int)p.query_offset; v.ql = (int)ql;
         all[i] = v;
-    });
+    }, total >> 20);   // (long sequences: one thread per MB rather than per 256 pairs)
     for (size_t i = 0; i < n; i++) if (e.pair_status[i] == TSA_OK) { e.live.push_back(i); e.views.push_back(all[i]); }
 }
 
@@ -413,7 +413,11 @@ int tsa_align_batch(const tsa_config* cfg, const tsa_options* opt, const tsa_pai
     const bool pipelined = o.descendant_strategy != 1;      // (the better of two searches is only known after both)
     auto run_engines = [&](const AlignOptions& ao, std::vector<PairCost>& costs) -> int {
 #ifndef TSA_EMUL
-    const bool split = live >= 4096 && !o.no_ts;
+    // (without template switches: batches of long pairs -- staging, the copy of the operations and the result assembly of one half
+    // then overlap the wavefront kernels of the other)
+    double job_cells = 0;
+    if (o.no_ts) for (size_t k = 0; k < live; k++) job_cells += (double)(enc.views[k].rl - enc.views[k].ro + 1) * (double)(enc.views[k].ql - enc.views[k].qo + 1);
+    const bool split = (live >= 4096 && !o.no_ts) || (o.no_ts && live >= 64 && job_cells >= 1.6e10);
 #else
     const bool split = false;   // the emulator is single-threaded
 #endif
