@@ -346,6 +346,7 @@ struct BandBatch {
     const int* prefix;       // [n_pairs + 1] first ticket of every pair
     int n_pairs;
     int* ticket;
+    const int* order;        // [2 * tickets] (entry of args, strip) of every ticket, or null: tickets in (pair, strip) order
 };
 
 // TRACE = false: forward passes of many pairs.  TRACE = true: many TILES (of one pair or several) recomputed with codes at once --
@@ -364,9 +365,14 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_ban
         if (lane == 0) tk = atomic_add_s32(bb.ticket, 1);
         tk = (int)shfl_idx((uint32_t)tk, 0);
         if (tk >= total) break;
-        int lo = 0, hi = bb.n_pairs - 1;                           // last pair whose first ticket is <= tk
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (bb.prefix[mid] <= tk) lo = mid; else hi = mid - 1; }
-        band_strip<TRACE>(bb.args[lo], bb.args[lo].s_lo + tk - bb.prefix[lo], cfg->A, subP, openP, extP);      // (the description stays in global memory: its fields are read once per strip)
+        int lo = 0, s = 0;
+        if (bb.order) { lo = bb.order[2 * tk]; s = bb.order[2 * tk + 1]; }
+        else {
+            int hi = bb.n_pairs - 1;                               // last pair whose first ticket is <= tk
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (bb.prefix[mid] <= tk) lo = mid; else hi = mid - 1; }
+            s = tk - bb.prefix[lo];
+        }
+        band_strip<TRACE>(bb.args[lo], bb.args[lo].s_lo + s, cfg->A, subP, openP, extP);      // (the description stays in global memory: its fields are read once per strip)
     }
 }
 

@@ -188,12 +188,14 @@ struct Engine::Impl {
     bool any_win = false;
     std::vector<int> h_winflag;
     DevBuf wave_prefix, wave_ticket;   // k_affine_wave: first ticket per pair, ticket counter
+    DevBuf wave_order;                 // (pair, strip) of every ticket: strip-major inside groups of pairs
     bool wave_ck = false;              // --no-ts with alignments through checkpoints (tsa_band.cuh: k_band_batch_*) instead of a code matrix
     DevBuf bb_args, bb_ckpt, bb_colck, bb_res, bb_tiles, bb_bnds;
     size_t bb_colck_bytes = 0;
     int bb_trace_blocks = 0;
     size_t scratch_bytes = 0;
     int wave_tickets = 0;
+    bool wave_ordered = false;
     std::vector<long long> h_ops_off; std::vector<int> h_ops_cap;
     size_t cells = 0, ops_total = 0;
     int max_m = 0, max_n = 0;            // longest query / reference of the staged chunk
@@ -329,7 +331,27 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         I.wave_prefix.ensure(prefix.size() * 4);
         I.wave_ticket.ensure(4);
         rt::h2d(I.wave_prefix.p, prefix.data(), prefix.size() * 4, I.stream);
-        rt::stream_sync(I.stream);   // `prefix` is a local
+        // Ticket order: strip-major inside groups of pairs (strip 0 of every pair of the group, then strip 1, ...).  The warps that run
+        // at the same time then work on DIFFERENT pairs whenever the batch has enough of them, and a strip starts when its left
+        // neighbour is (nearly) done instead of running 32 rows behind it: the boundary polls of the (pair, strip) order -- a fifth
+        // of the issued instructions and a quarter of the stall samples of the forward pass, profiles/r02_k_band_batch_forward_* --
+        // succeed at once.  The boundary column of a pair then lives in L2 / HBM between two of its strips (16 B per row and strip).
+        std::vector<int> order;
+        if (I.list_all.size() > 1 && !I.opt.pair_major_wave) {
+            order.reserve((size_t)prefix.back() * 2);
+            const size_t G = 8192;
+            for (size_t g0 = 0; g0 < I.list_all.size(); g0 += G) {
+                const size_t g1 = std::min(I.list_all.size(), g0 + G);
+                int smax = 0;
+                for (size_t k = g0; k < g1; k++) smax = std::max(smax, prefix[k + 1] - prefix[k]);
+                for (int s = 0; s < smax; s++)
+                    for (size_t k = g0; k < g1; k++) if (s < prefix[k + 1] - prefix[k]) { order.push_back((int)k); order.push_back(s); }
+            }
+            I.wave_order.ensure(order.size() * 4);
+            rt::h2d(I.wave_order.p, order.data(), order.size() * 4, I.stream);
+        }
+        I.wave_ordered = !order.empty();
+        rt::stream_sync(I.stream);   // `prefix`, `order` are locals
     }
     size_t bb_bytes = 0;
     std::vector<size_t> bb_ckpt_off, bb_colck_off;
@@ -826,6 +848,7 @@ void Engine::run_wave() {
     WaveArgs wa;
     wa.list = I.d_list_all; wa.n_list = n_all; wa.strip_prefix = I.wave_prefix.as<int>();
     wa.ticket = I.wave_ticket.as<int>();
+    wa.order = I.wave_ordered ? I.wave_order.as<int>() : nullptr;
     const size_t smem = (size_t)WAVE_SMEM_INTS * sizeof(int);
     int blocks = (I.wave_tickets + WAVE_WARPS - 1) / WAVE_WARPS;
 #ifndef TSA_EMUL
@@ -856,6 +879,7 @@ void Engine::run_wave() {
         rt::stream_sync(I.stream);   // `res_init` is a local
         BandBatch bb;
         bb.args = I.bb_args.as<BandArgs>(); bb.pair_of = I.d_list_all; bb.prefix = I.wave_prefix.as<int>(); bb.n_pairs = n_all; bb.ticket = I.wave_ticket.as<int>();
+        bb.order = I.wave_ordered ? I.wave_order.as<int>() : nullptr;
         TSA_LAUNCH(k_band_batch<false>, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), smem, I.stream, I.cfg.as<DevConfig>(), bb);
         TSA_LAUNCH(k_band_batch_finish, dim3((unsigned)((n_all + 255) / 256)), dim3(256), 0, I.stream, I.ck, bb);
         stats_.launches += 2; stats_.fill_launches++;
@@ -923,7 +947,7 @@ void Engine::run_trace() {
         I.bb_tiles.ensure(warps * (size_t)bt.tile_bytes); I.bb_bnds.ensure(warps * (size_t)(BB_INTERVAL + 1) * sizeof(WaveBnd));
         bt.tiles = I.bb_tiles.as<uint8_t>(); bt.bnds = I.bb_bnds.as<WaveBnd>();
         BandBatch bb;
-        bb.args = I.bb_args.as<BandArgs>(); bb.pair_of = I.d_list_all; bb.prefix = I.wave_prefix.as<int>(); bb.n_pairs = n_all; bb.ticket = I.wave_ticket.as<int>();
+        bb.args = I.bb_args.as<BandArgs>(); bb.pair_of = I.d_list_all; bb.prefix = I.wave_prefix.as<int>(); bb.n_pairs = n_all; bb.ticket = I.wave_ticket.as<int>(); bb.order = nullptr;
         if (n_all) { TSA_LAUNCH(k_band_batch_trace, dim3((unsigned)blocks), dim3(32 * WAVE_WARPS), (size_t)WAVE_SMEM_INTS * sizeof(int), I.stream, I.cfg.as<DevConfig>(), I.ck, bb, bt, to); l++; }
     } else if (!I.ts_enabled) {
         launch_trace<3, false>(I.ck, tl, to, I.rows, I.d_list_all, (int)I.list_all.size(), 0, dev_.A, I.stream, l);

@@ -321,7 +321,7 @@ void LongPair::speculate(size_t budget_bytes) {
     rt::dev_memset(I.sp_bnds.p, 0xff, T * (size_t)(IV + 1) * sizeof(WaveBnd), I.stream);
     rt::stream_sync(I.stream);   // `args`, `prefix` are locals
     BandBatch bb;
-    bb.args = I.sp_args.as<BandArgs>(); bb.pair_of = nullptr; bb.prefix = I.sp_prefix.as<int>(); bb.n_pairs = (int)T; bb.ticket = I.sp_prefix.as<int>() + T + 1;
+    bb.args = I.sp_args.as<BandArgs>(); bb.pair_of = nullptr; bb.prefix = I.sp_prefix.as<int>(); bb.n_pairs = (int)T; bb.ticket = I.sp_prefix.as<int>() + T + 1; bb.order = nullptr;
     const int blocks = std::min(I.resident_blocks, (prefix[T] + WAVE_WARPS - 1) / WAVE_WARPS);
 #ifndef TSA_EMUL
     rt::check(cudaEventRecord(I.ev[0], I.stream), "cudaEventRecord");

@@ -45,6 +45,7 @@ struct WaveArgs {
     int n_list;
     const int* strip_prefix; // [n_list + 1] first ticket of every pair
     int* ticket;             // next strip to hand out
+    const int* order;        // [2 * tickets] (pair index in list, strip) of every ticket, or null: tickets in (pair, strip) order
 };
 
 struct alignas(8) WaveBnd { uint32_t nd, i; };      // boundary entry: values in bits 0..25, tag bits 0-5 in nd[26..31], tag bits 6-11 in i[26..31]
@@ -96,9 +97,14 @@ TSA_KERNEL void TSA_LAUNCH_BOUNDS(32 * WAVE_WARPS, TSA_WAVE_BLOCKS_PER_SM) k_aff
         if (lane == 0) tk = atomic_add_s32(wa.ticket, 1);
         tk = (int)shfl_idx((uint32_t)tk, 0);
         if (tk >= total) break;
-        int lo = 0, hi = wa.n_list - 1;                           // last pair whose first ticket is <= tk
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (wa.strip_prefix[mid] <= tk) lo = mid; else hi = mid - 1; }
-        const int b = wa.list[lo], s = tk - wa.strip_prefix[lo];
+        int lo = 0, s = 0;
+        if (wa.order) { lo = wa.order[2 * tk]; s = wa.order[2 * tk + 1]; }
+        else {
+            int hi = wa.n_list - 1;                                // last pair whose first ticket is <= tk
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (wa.strip_prefix[mid] <= tk) lo = mid; else hi = mid - 1; }
+            s = tk - wa.strip_prefix[lo];
+        }
+        const int b = wa.list[lo];
         const PairMeta pm = ck.pairs[b];
         const int nn = pm.rl - pm.ro, mm = pm.ql - pm.qo;         // the alignment range is the matrix
         const uint8_t* R = ck.seq + pm.seq_r + pm.ro;

@@ -83,11 +83,11 @@ def main():
     shapes = args or ["c4", "c5", "c3"]
     n_pairs = int(sys.argv[sys.argv.index("--pairs") + 1]) if "--pairs" in sys.argv else None
     text = workloads.sample_config_text()
-    dev_flags = int(sys.argv[sys.argv.index("--dev-flags") + 1]) if "--dev-flags" in sys.argv else 0   # 128: one warp per pair in the primary fill; 32: fused first window stage
+    dev_flags = int(sys.argv[sys.argv.index("--dev-flags") + 1]) if "--dev-flags" in sys.argv else 0   # 128: one warp per pair in the primary fill; 32: fused first window stage; 256: --no-ts strips in (pair, strip) ticket order
     if "c4" in shapes:
         pairs = [workloads.long_pair(i, 10000) for i in range(n_pairs or 1024)]
         for tb in (False, True):
-            measure(f"c4: 10 kb pairs, --no-ts, alignments={tb}", tsa.Aligner(costs=text, no_ts=True, traceback=tb), pairs)
+            measure(f"c4: 10 kb pairs, --no-ts, alignments={tb}", tsa.Aligner(costs=text, no_ts=True, traceback=tb, dev_flags=dev_flags), pairs, extra={"dev_flags": dev_flags})
     if "c5" in shapes:
         pair = c5_pair()
         for tb in (False, True):
