@@ -138,6 +138,7 @@ TSA_DEV void band_strip(const BandArgs& ba, int s, int A, const int* subP, const
         const int steps = (row1 - row0) + 32;
         int* const ck_out = ba.ckpt_out;
         const int ck_interval = imax(ba.interval, 1);
+        const int ck_shift = (ck_interval & (ck_interval - 1)) == 0 ? 31 - clz_u32((uint32_t)ck_interval) : -1;   // power of two: no division per checkpoint row
         const long long dstride = ba.dstride;
         const int row_base = ba.row_base;
         const bool local_out = bnd_wr != nullptr && bnd_wr == ba.bnd_local;
@@ -209,7 +210,7 @@ TSA_DEV void band_strip(const BandArgs& ba, int s, int A, const int* subP, const
             }
             if (store_ck) {
                 // checkpoint row: M, Dl, min(N, I) of every column, from the registers the next row reads
-                int* ck_row = ck_out + (long long)(i / ck_interval - 1) * ba.ckpt_stride;
+                int* ck_row = ck_out + (long long)((ck_shift >= 0 ? i >> ck_shift : i / ck_interval) - 1) * ba.ckpt_stride;
                 if (lane == 0 && j0 == ba.ck_col0) { ck_row[0] = imin(lnd, li); ck_row[1] = INF32; ck_row[2] = INF32; }   // the column left of the band
 #pragma unroll
                 for (int c = 0; c < CB; c++) if (j0 + c <= mm) {
