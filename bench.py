@@ -252,8 +252,33 @@ def sub_records(which, lib, device, steps):
             pairs = c4_pairs(2048)
             out["c4"] = batch_record(tsa.Aligner(costs=text, no_ts=True, traceback=True, device=device, lib=lib), pairs, lambda n, m, k: 7.0 * n * m, s32.value,
                                      "k_band_batch_forward + k_band_batch_trace", "configs[3] shape: 2048 synthetic 10 kb pairs per step (1 % substitutions, 0.5 % indels), --no-ts, alignments returned (checkpoint rows + recomputed tiles, no code matrix)")
+            # the same batch, costs only (k_affine_wave<false>): the wavefront kernel by itself
+            staged = tsa.StagedBatch(tsa.Aligner(costs=text, no_ts=True, traceback=False, device=device, lib=lib), pairs)
+            staged.run()
+            t = time.perf_counter()
+            for _ in range(steps):
+                staged.run()
+            dt = (time.perf_counter() - t) / steps
+            staged.close()
+            cells = sum(len(r) * len(q) for r, q in pairs)
+            out["c4"]["costs_only"] = {"value": cells / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3, "kernel": "k_affine_wave<false>",
+                                       "roofline_frac": 7.0 * cells / dt / s32.value}
         except Exception as exc:  # noqa: BLE001
             out["c4"] = {"error": repr(exc)}
+    if "ts_long" in which:
+        try:
+            # one pair with template switches beyond every whole-sequence class (column windows + tiled stage), through the C ABI
+            pair = workloads.long_pair(41, 3000, sub_rate=0.004, indel_rate=0.002, n_tsm=4)
+            aligner = tsa.Aligner(costs=text, device=device, lib=lib)
+            t = time.perf_counter()
+            g = aligner.align_batch([pair])[0]
+            dt = time.perf_counter() - t
+            out["ts_long"] = {"workload": "one 3 kb pair with 4 planted TSMs (0.4 % substitutions, 0.2 % indels), template switches on, alignment returned; single cold call",
+                              "status": g.status, "cost": g.cost, "template_switches": g.template_switches, "seconds": dt,
+                              "value": len(pair[0]) * len(pair[1]) / dt / 1e9, "unit": UNIT}
+            del aligner
+        except Exception as exc:  # noqa: BLE001
+            out["ts_long"] = {"error": repr(exc)}
     if "c3" in which:
         try:
             ftext = text.replace("left_flank_length = 0", "left_flank_length = 50").replace("right_flank_length = 0", "right_flank_length = 50")
@@ -465,7 +490,7 @@ def run_ours(args):
                      "note": "per step: chain pairs started / surviving chain-level pruning, chain rows filled (2 chains x 160 columns each), "
                              "rows whose jump-in/jump-out was evaluated; the dense formula of SURVEY 8(d) assumes 99 rows per chain"},
             "alignments": "every pair returns its run-length encoded alignment (traceback kernel inside the timed step)"}
-    which = [c for c in (args.configs if args.configs is not None else ("c4,c3,c5" if world == 1 else "")).split(",") if c]
+    which = [c for c in (args.configs if args.configs is not None else ("c4,c3,c5,ts_long" if world == 1 else "")).split(",") if c]
     if which:
         del aligner          # frees the engines (device buffers) of the headline workload
         __import__("gc").collect()
@@ -486,7 +511,7 @@ def main():
     ap.add_argument("--first-threshold", type=int, default=0, help="tuning knob of the exact pruning (0 = library default)")
     ap.add_argument("--scout", action="store_true", help="tuning knob: enable the reverse-kinds scouting round")
     ap.add_argument("--cpu-budget", type=float, default=18.0, help="sizes the live part of the CPU A* replay: pairs of the fixed sample that took at most a third of this offline")
-    ap.add_argument("--configs", default=None, help="comma list of sub-records (c3,c4,c5) added under extra.configs; default: all three at --gpus 1, none otherwise")
+    ap.add_argument("--configs", default=None, help="comma list of sub-records (c3,c4,c5,ts_long) added under extra.configs; default: all four at --gpus 1, none otherwise")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
