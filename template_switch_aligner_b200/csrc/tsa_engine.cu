@@ -234,7 +234,7 @@ Engine::Engine(const HostConfig& cfg, int device) : impl_(new Impl), host_(cfg) 
     if (device < 0 || device >= count) { err_ = "invalid CUDA device index"; return; }
     rt::check(cudaSetDevice(device), "cudaSetDevice");
     rt::check(cudaStreamCreateWithFlags(&impl_->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-    for (auto& e : impl_->ev) rt::check(cudaEventCreate(&e), "cudaEventCreate");
+    for (auto& e : impl_->ev) rt::check(cudaEventCreateWithFlags(&e, rt::event_flags()), "cudaEventCreate");
 #endif
     impl_->cfg.ensure(sizeof(DevConfig));
     rt::h2d(impl_->cfg.p, &dev_, sizeof(DevConfig), impl_->stream);

@@ -159,7 +159,7 @@ LongPair::LongPair(const HostConfig& cfg, int device, const uint8_t* R, const ui
     if (device < 0 || device >= count) { err_ = "invalid CUDA device index"; return; }
     rt::check(cudaSetDevice(device), "cudaSetDevice");
     rt::check(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-    for (auto& e : I.ev) rt::check(cudaEventCreate(&e), "cudaEventCreate");
+    for (auto& e : I.ev) rt::check(cudaEventCreateWithFlags(&e, rt::event_flags()), "cudaEventCreate");
     {
         cudaDeviceProp prop;
         rt::check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");

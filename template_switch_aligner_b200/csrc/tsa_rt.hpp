@@ -10,6 +10,8 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
+#include <algorithm>
 #include <cstring>
 
 #ifndef TSA_EMUL
@@ -215,7 +217,29 @@ inline void dev_free(void* p) { if (p) cudaFree(p); }
 inline void h2d(void* d, const void* h, size_t bytes, cudaStream_t s) { check(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s), "h2d"); }
 inline void d2h(void* h, const void* d, size_t bytes, cudaStream_t s) { check(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s), "d2h"); }
 inline void dev_memset(void* d, int byte, size_t bytes, cudaStream_t s) { check(cudaMemsetAsync(d, byte, bytes, s), "memset"); }
-inline void stream_sync(cudaStream_t s) { check(cudaStreamSynchronize(s), "stream sync"); }
+// Waiting host threads: the CUDA default spins on a core.  When several ranks share the host (one process per GPU, two engine
+// threads each) the spinning threads take the cores the result assembly needs, so the waits then block on an event created with
+// cudaEventBlockingSync instead (TSA_B200_BLOCKING_SYNC=0/1 overrides; automatic: ranks of the launch x 4 >= host cores; measured on one GPU: no difference).
+inline bool blocking_sync() {
+    static const bool on = []() {
+        if (const char* e = getenv("TSA_B200_BLOCKING_SYNC")) return atoi(e) != 0;
+        long ranks = 1;
+        if (const char* w = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1L, atol(w));
+        return ranks * 4 >= (long)std::max(1u, std::thread::hardware_concurrency());
+    }();
+    return on;
+}
+inline unsigned event_flags() { return blocking_sync() ? (unsigned)cudaEventBlockingSync : (unsigned)cudaEventDefault; }
+inline void stream_sync(cudaStream_t s) {
+    if (!blocking_sync()) { check(cudaStreamSynchronize(s), "stream sync"); return; }
+    thread_local cudaEvent_t ev[64] = {};
+    int dev = 0;
+    check(cudaGetDevice(&dev), "cudaGetDevice");
+    cudaEvent_t& e = ev[dev & 63];
+    if (!e) check(cudaEventCreateWithFlags(&e, cudaEventBlockingSync | cudaEventDisableTiming), "cudaEventCreateWithFlags");
+    check(cudaEventRecord(e, s), "cudaEventRecord");
+    check(cudaEventSynchronize(e), "event sync");
+}
 inline void* host_alloc(size_t bytes) { void* p = nullptr; check(cudaMallocHost(&p, bytes ? bytes : 1), "cudaMallocHost"); return p; }
 inline void host_free(void* p) { if (p) cudaFreeHost(p); }
 #else
