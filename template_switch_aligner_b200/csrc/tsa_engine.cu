@@ -468,6 +468,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.band = I.any_win ? I.band.as<int>() : nullptr;
     ck.winflag = I.any_win ? I.winflag.as<int>() : nullptr;
     ck.win_stage = 0;
+    ck.seeds_merged = 0;
     rt::stream_sync(I.stream);
     return true;
 }
@@ -504,16 +505,29 @@ void Engine::run_staged() {
             I.ck.dir = I.dirL[layer]->as<uint8_t>();
             if (I.ts_enabled) { I.DL[layer]->ensure(I.cells * 2); I.ck.D = I.DL[layer]->as<int16_t>(); }
         }
+        // Pairs of several column blocks: one CTA per pair, the blocks pipelined over its warps; the reentry seeds of both
+        // orientations are merged into seedA first (coalesced tiles on all SMs) so that the fill reads one contiguous row.
+        auto wide = [&](auto kern, int warps) {
+            Chunk ckm = I.ck;
+            if (layer > 0 && !I.ck.pl_in) {
+                const int tiles = ((I.max_n + 32) / 32) * ((I.max_m + 32) / 32);
+                for (int off = 0; off < cnt; off += 65535) {
+                    const int c2 = std::min(65535, cnt - off);
+                    TSA_LAUNCH(k_merge_seeds, dim3((unsigned)std::min(tiles, 2048), (unsigned)c2), dim3(256), (size_t)32 * 33 * sizeof(int), I.stream, I.ck, d_list + off, c2);
+                    stats_.launches++;
+                }
+                ckm.seeds_merged = 1;
+            }
+            TSA_LAUNCH(kern, dim3((unsigned)cnt), dim3(32 * warps), (size_t)(warps * K1_SMEM_INTS + 1) * sizeof(int), I.stream, ckm, d_list, cnt, layer);
+        };
 #ifdef TSA_EMUL
         if ((I.opt.test_small_windows || I.opt.test_tiled) && I.ts_enabled && I.max_m + 1 > 32)   // CPU tests of the pipelined fill: 32-column blocks
-            TSA_LAUNCH((k_primary_fill<1, 4>), dim3((unsigned)cnt), dim3(32 * 4), (size_t)(4 * K1_SMEM_INTS + 1) * sizeof(int), I.stream, I.ck, d_list, cnt, layer);
+            wide(k_primary_fill<1, 4>, 4);
         else
 #endif
         if (I.max_m + 1 <= 32 * 5) TSA_LAUNCH(k_primary_fill<5>, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
-        else if (I.max_m + 1 > 32 * K1_CB * 4 && !I.opt.narrow_fill)   // several column blocks per pair: one CTA per pair, the blocks pipelined over its warps
-            TSA_LAUNCH((k_primary_fill<K1_CB, K1_WIDE_MAX>), dim3((unsigned)cnt), dim3(32 * K1_WIDE_MAX), (size_t)(K1_WIDE_MAX * K1_SMEM_INTS + 1) * sizeof(int), I.stream, I.ck, d_list, cnt, layer);
-        else if (I.max_m + 1 > 32 * K1_CB && !I.opt.narrow_fill)
-            TSA_LAUNCH((k_primary_fill<K1_CB, 4>), dim3((unsigned)cnt), dim3(32 * 4), (size_t)(4 * K1_SMEM_INTS + 1) * sizeof(int), I.stream, I.ck, d_list, cnt, layer);
+        else if (I.max_m + 1 > 32 * K1_CB * 4 && !I.opt.narrow_fill) wide(k_primary_fill<K1_CB, K1_WIDE_MAX>, K1_WIDE_MAX);
+        else if (I.max_m + 1 > 32 * K1_CB && !I.opt.narrow_fill) wide(k_primary_fill<K1_CB, 4>, 4);
         else TSA_LAUNCH(k_primary_fill<K1_CB>, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
         stats_.launches++; stats_.fill_launches++;
     };

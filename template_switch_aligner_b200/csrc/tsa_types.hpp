@@ -130,6 +130,7 @@ struct Chunk {
                              // D < thr - min_ts (the only cells a template switch below the threshold can start from); null: unused
     int* winflag;            // [pair] bit 0: a chain's window did not fit the first-stage class in this layer (redo in the second
                              // stage); bit 1: it did not fit the widest class either (the pair is refused)
+    int seeds_merged;        // 1: seedA already holds min(seedA, seedB transposed) (k_merge_seeds): the primary fill reads seedA only
     int win_stage;           // 0: not a windowed launch; 1: first stage; 2: second stage (only pairs with bit 0 set)
     // ---- row queue between the row kernel and the evaluation kernel (pairs that run without column windows) ---------------
     int* q_count;            // slots reserved in this launch (may exceed q_cap: the host then repeats the layer with smaller slices)
