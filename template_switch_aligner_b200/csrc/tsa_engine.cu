@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <chrono>
 #include <cstring>
 #include <stdexcept>
@@ -27,8 +28,9 @@ struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     void ensure(size_t bytes) {
-        if (bytes > cap) { rt::dev_free(p); p = rt::dev_alloc(bytes); cap = bytes; }
+        if (bytes > cap) { rt::dev_free(p); p = nullptr; cap = 0; p = rt::dev_alloc(bytes); cap = bytes; }   // (an allocation that throws leaves the buffer empty)
     }
+    void reset() { rt::dev_free(p); p = nullptr; cap = 0; }
     ~DevBuf() { rt::dev_free(p); }
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
@@ -38,7 +40,7 @@ struct HostBuf {
     void* p = nullptr;
     size_t cap = 0;
     void ensure(size_t bytes) {
-        if (bytes > cap) { rt::host_free(p); p = rt::host_alloc(bytes); cap = bytes; }
+        if (bytes > cap) { rt::host_free(p); p = nullptr; cap = 0; p = rt::host_alloc(bytes); cap = bytes; }
     }
     ~HostBuf() { rt::host_free(p); }
     template <class T> T* as() const { return static_cast<T*>(p); }
@@ -47,13 +49,16 @@ struct HostBuf {
 #ifndef TSA_EMUL
 // Function attributes (dynamic shared memory opt-in) are per device: one flag per (kernel instantiation, device).
 struct PerDeviceOnce {
-    std::atomic<bool> done[64];
-    PerDeviceOnce() { for (auto& d : done) d = false; }
-    bool first() {
+    std::mutex mu;
+    bool done[64] = {};
+    // Runs `init` once per device; a concurrent caller (the second engine thread of a call) waits until it has finished, so that
+    // no kernel is launched before its attributes are set.
+    template <class F> void run(F&& init) {
         int dev = 0;
         cudaGetDevice(&dev);
-        if (dev < 0 || dev >= 64) return true;
-        return !done[dev].exchange(true);
+        dev &= 63;
+        std::lock_guard<std::mutex> guard(mu);
+        if (!done[dev]) { init(); done[dev] = true; }
     }
 };
 #endif
@@ -91,7 +96,7 @@ void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len
     const size_t smem = jump_smem_per_warp(A, C) * warps;
 #ifndef TSA_EMUL
     static PerDeviceOnce once;
-    if (once.first()) {
+    once.run([&] {
         rt::check(cudaFuncSetAttribute(k_ts_jump<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
         rt::check(cudaFuncSetAttribute(k_ts_jump<C, WIN>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "cudaFuncSetAttribute");
         if (getenv("TSA_B200_DEBUG")) {
@@ -101,7 +106,7 @@ void launch_jump(Chunk ck, int stage, const int* d_list, int n_list, int max_len
             cudaFuncGetAttributes(&fa, k_ts_jump<C, WIN>);
             fprintf(stderr, "[tsalign_b200] k_ts_jump<%d,%d>: %d regs, %zu B dynamic smem/block, %d blocks/SM resident\n", C, (int)WIN, fa.numRegs, smem, blocks);
         }
-    }
+    });
 #endif
     const int n_ep = (max_len - ml + 2) / 2;
     if (n_ep <= 0 || n_kinds <= 0) return;
@@ -129,7 +134,7 @@ void launch_jump_split(Chunk ck, int stage, const int* d_list, int n_list, int m
     static std::atomic<int> resident[64];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (once.first()) {
+    once.run([&] {
         auto row = k_ts_jump<C, WIN, true>;
         auto eval = k_ts_eval<C, WIN>;
         rt::check(cudaFuncSetAttribute(row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
@@ -148,7 +153,7 @@ void launch_jump_split(Chunk ck, int stage, const int* d_list, int n_list, int m
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&row_blocks, row, 32 * warps, smem_row);
             fprintf(stderr, "[tsalign_b200] C=%d windows=%d: row kernel %d regs, %d blocks/SM; eval kernel %d regs, %d blocks/SM\n", C, (int)WIN, fa.numRegs, row_blocks, fb.numRegs, per_sm);
         }
-    }
+    });
     eval_blocks = resident[dev & 63];
 #endif
     const int n_ep = (max_len - ml + 2) / 2;
@@ -177,6 +182,12 @@ struct Engine::Impl {
     cudaStream_t stream = 0;
     std::vector<DevBuf*> dirL, DL;       // per-layer traceback codes / D matrices (traceback only)
     std::vector<DevBuf*> fdL, dir2L;     // flank mode: per-layer codes of the flank planes / seed flags of plane 0
+    size_t budget_hint = 0;              // chunk budget of the first large job (the buffers of that size stay allocated)
+    int layers_seen = 8;                 // most layers a chunk of this engine has kept so far (chunk sizing)
+    void release_layers() {              // after an allocation failure: give the per-layer buffers and the row queue back
+        for (auto* v : {&dirL, &DL, &fdL, &dir2L}) { for (DevBuf* b : *v) delete b; v->clear(); }
+        q_rows.reset(); q_hdr.reset();
+    }
     DevBuf PA, PB, tgt_key, best_plane;  // flank mode: ping-pong state planes, per-layer target keys
     bool flank = false;
     DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b, tables;
@@ -555,7 +566,7 @@ void Engine::run_staged() {
         auto run = [&](int16_t*& src, int16_t*& dst, int table, int plane0, int count, int final_at_end, int no_report_plane) {
 #ifndef TSA_EMUL
             static PerDeviceOnce once;
-            if (once.first()) rt::check(cudaFuncSetAttribute(k_flank_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLANK_SMEM), "cudaFuncSetAttribute");
+            once.run([&] { rt::check(cudaFuncSetAttribute(k_flank_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLANK_SMEM), "cudaFuncSetAttribute"); });
 #endif
             for (int done = 0; done < count; done += FLANK_FS) {
                 const int ns = std::min(FLANK_FS, count - done);
@@ -918,7 +929,7 @@ static void launch_trace(const Chunk& ck, const TraceLayers& tl, TraceOut to, De
     const size_t smem = jump_smem_per_warp(A, C) * warps;
 #ifndef TSA_EMUL
     static PerDeviceOnce once;
-    if (once.first()) rt::check(cudaFuncSetAttribute(k_traceback<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute");
+    once.run([&] { rt::check(cudaFuncSetAttribute(k_traceback<C, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)227 * 1024)), "cudaFuncSetAttribute"); });
 #endif
     const long long stride = (long long)(rows_max + 1) * 3 * 32 * C;   // shorts per warp
     const long long budget = (long long)1 << 29;                        // 1 GiB of shorts-pairs scratch per slice
@@ -1061,7 +1072,10 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
         size_t free_b = 0, total_b = 0;
         rt::check(cudaSetDevice(impl_->device), "cudaSetDevice");
         rt::check(cudaMemGetInfo(&free_b, &total_b), "cudaMemGetInfo");
-        budget = std::max<size_t>((size_t)1 << 30, free_b / 3);   // a second engine may be working on the other half of the batch
+        // a second engine may be working on the other half of the batch; what this engine sized its buffers for earlier is still its own
+        // (a third of what is free once the row queues of two engines, up to 16 GiB each, are set aside)
+        budget = std::max<size_t>(std::max<size_t>((size_t)1 << 30, (free_b - std::min<size_t>(free_b / 4, (size_t)32 << 30)) / 3), impl_->budget_hint);
+        impl_->budget_hint = budget;
 #else
         budget = (size_t)1 << 30;
 #endif
@@ -1082,7 +1096,8 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
             return b + std::max<size_t>(1, nn / BB_INTERVAL) * (mm + 2) * 12 + (size_t)((wave_strips((int)mm + 1) + BB_GROUP - 1) / BB_GROUP) * (nn + 1) * 8
                      + 3 * (size_t)(p.n + p.m) + 256;
         }
-        if (opt.traceback) b += cells * ((!opt.no_ts && dev_.n_kinds > 0) ? 9 : 1) + 3 * (size_t)(p.n + p.m) + 256;   // codes (+ D) of ~3 layers, ops
+        // codes (+ D) of every layer a pair of the chunk reaches (3 B per cell and layer; the deepest chunk so far decides), ops
+        if (opt.traceback) b += cells * ((!opt.no_ts && dev_.n_kinds > 0) ? 3 * (size_t)(impl_->layers_seen + 1) : 1) + 3 * (size_t)(p.n + p.m) + 256;
         if (!opt.no_ts && dev_.n_kinds > 0 && (dev_.left_flank > 0 || dev_.right_flank > 0))   // flank planes, and their codes of ~4 layers
             b += cells * (12 + (opt.traceback ? (size_t)(dev_.left_flank + dev_.right_flank + 1) * 4 : 0));
         return b;
@@ -1114,15 +1129,35 @@ void Engine::align_costs(const PairView* pairs, size_t n, const AlignOptions& op
         AlignOptions o = opt;
         if (job_ck) o.wave_checkpoints = std::max(o.wave_checkpoints, 1);
         o.chunk_bytes = (size_t)1 << 62;   // the chunk was sized above; stage() must not refuse it
-        if (!stage(pairs + i, j - i, o)) {
+        std::chrono::steady_clock::time_point c0, c1;
+        bool refused = false;
+        for (;;) {
+            // The layers a pair needs are only known afterwards: a chunk whose pairs go deeper than estimated may not fit.  It is
+            // then redone at half the size with the per-layer buffers released (nothing of it was handed out yet).
+            try {
+                if (!stage(pairs + i, j - i, o)) { refused = true; break; }
+                c0 = std::chrono::steady_clock::now();
+                run_staged();
+                c1 = std::chrono::steady_clock::now();
+                fetch_staged(out + i);
+                break;
+            } catch (const std::runtime_error& e) {
+                if (std::string(e.what()).find("out of memory") == std::string::npos || j - i < 2) throw;
+#ifndef TSA_EMUL
+                cudaGetLastError();
+                cudaStreamSynchronize(impl_->stream);
+#endif
+                impl_->release_layers();
+                if (getenv("TSA_B200_DEBUG")) fprintf(stderr, "[tsalign_b200] chunk of %zu pairs did not fit (%s): redone at half the size\n", j - i, e.what());
+                j = i + (j - i) / 2;
+            }
+        }
+        if (refused) {
             for (size_t k = i; k < j; k++) { out[k] = PairCost(); out[k].status = PAIR_ERR_TOO_LONG; }
             i = j;
             continue;
         }
-        const auto c0 = std::chrono::steady_clock::now();
-        run_staged();
-        const auto c1 = std::chrono::steady_clock::now();
-        fetch_staged(out + i);
+        impl_->layers_seen = std::max(impl_->layers_seen, stats_.layers_run);
         if (getenv("TSA_B200_DEBUG"))
             fprintf(stderr, "[tsalign_b200] chunk of %zu pairs: stage %.2f ms, run %.2f ms, fetch %.2f ms\n", j - i,
                     1e3 * std::chrono::duration<double>(c0 - cs).count(), 1e3 * std::chrono::duration<double>(c1 - c0).count(),
