@@ -192,6 +192,8 @@ struct Engine::Impl {
     bool flank = false;
     DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b, tables;
     DevBuf band, winflag;                             // column windows: band vectors of the fill, overflow flags
+    DevBuf cpflag;                                    // ... and the chain-pair bitmaps of the long class
+    size_t cpflag_ints = 0;
     DevBuf q_hdr, q_rows, q_counts;                   // row queue between the row kernel and the evaluation kernel
     size_t q_cap = 0;                                 // slots
     double q_est[N_CLASS][2][3] = {};                 // learned demand of queue slots per pair, by class, first / later deepening round and
@@ -285,7 +287,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.any_win = false;
     for (auto& l : I.class_list) l.clear();
     for (auto& v : I.class_maxlen) v = 0;
-    size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0, tab = 0;
+    size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0, tab = 0, cpf_ints = 0;
     I.max_m = 0; I.max_n = 0;
     I.wave_ck = false;
     if (!I.ts_enabled && opt.traceback && n > 0 && opt.wave_checkpoints >= 0) {
@@ -310,7 +312,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
 #endif
         pm.scr = (long long)scr; scr += ((3 * ((size_t)pv.n + 1) + 1) & ~(size_t)1) * (wide_fill ? K1_WIDE_MAX : 1);
         pm.mat = (long long)cells;
-        pm.tab = -1; pm.lw = 0;
+        pm.tab = -1; pm.lw = 0; pm.cpf = -1; pm.cpf_words = 0;
         const int W = std::max(pv.n, pv.m) + 1;
         if (I.ts_enabled) {
             if (dev_.left_flank + dev_.right_flank + 1 >= KEY_PLANES) { I.status[i] = PAIR_ERR_FLANKS; continue; }
@@ -324,6 +326,11 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
             I.class_maxlen[cls] = std::max(I.class_maxlen[cls], W - 1);
             pm.lw = cls == N_CLASS - 1 ? (W + 7) & ~7 : 32 * CLASS_C[cls];
             pm.win = (cls == 4 && !opt.no_windows) || cls == 5 ? 1 : 0;
+            if (cls == N_CLASS - 1 && dev_.ml >= 0 && W - 1 >= dev_.ml) {
+                const size_t n_ep = (size_t)((W - 1 - dev_.ml + 2) / 2);
+                pm.cpf_words = (int)(((size_t)dev_.n_kinds * n_ep + 31) / 32);
+                pm.cpf = (long long)cpf_ints; cpf_ints += 2 * (size_t)pm.cpf_words;
+            }
             if (pm.win) I.any_win = true;
             pm.tab = (long long)tab;
             tab += 4 * table_bytes(dev_.A, pm.lw);
@@ -409,7 +416,8 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.counters.ensure(64);
     I.thr.ensure(n * 4); I.ub.ensure(n * 4); I.t0.ensure(n * 4); I.resolved.ensure(n * 4); I.capped.ensure(n * 4);
     if (I.ts_enabled) { I.D.ensure(cells * 2); I.DT.ensure(cells * 2); I.seedA.ensure(cells * 4); I.seedB.ensure(cells * 4); }
-    if (I.any_win) { I.band.ensure(vec * 8); I.winflag.ensure(n * 4); }
+    if (I.any_win) { I.band.ensure(vec * 8); I.winflag.ensure(n * 4); I.cpflag.ensure(cpf_ints * 4 + 4); }
+    I.cpflag_ints = cpf_ints;
     if (I.flank) { I.PA.ensure(cells * 6); I.PB.ensure(cells * 6); I.tgt_key.ensure(n * 4); I.best_plane.ensure(n * 4); }
     if (opt.traceback) {
         I.ops.ensure(I.ops_total); I.ops_off.ensure(n * 8); I.ops_cap.ensure(n * 4); I.ops_len.ensure(n * 4);
@@ -478,6 +486,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.flank_mode = I.flank ? 1 : 0;
     ck.band = I.any_win ? I.band.as<int>() : nullptr;
     ck.winflag = I.any_win ? I.winflag.as<int>() : nullptr;
+    ck.cpflag = I.any_win && I.cpflag_ints ? I.cpflag.as<int>() : nullptr;
     ck.win_stage = 0;
     ck.seeds_merged = 0;
     rt::stream_sync(I.stream);
@@ -501,6 +510,7 @@ void Engine::run_staged() {
     rt::dev_memset(I.capped.p, 0, I.npairs * 4, I.stream);
     if (!I.ts_enabled) { run_wave(); run_trace(); return; }
     if (I.any_win) rt::dev_memset(I.winflag.p, 0, I.npairs * 4, I.stream);
+    if (I.any_win && I.cpflag_ints) rt::dev_memset(I.cpflag.p, 0, I.cpflag_ints * 4, I.stream);
 #ifndef TSA_EMUL
     auto mark = [&](int k) { rt::check(cudaEventRecord(I.ev[k], I.stream), "cudaEventRecord"); };
     auto span = [&](int a, int b) { float ms = 0; rt::check(cudaEventSynchronize(I.ev[b]), "cudaEventSynchronize"); cudaEventElapsedTime(&ms, I.ev[a], I.ev[b]); return (double)ms; };
