@@ -211,6 +211,7 @@ AlignOptions engine_options(const tsa_options& o) {
     a.scout_round = (o.reserved & 1) != 0;   // bit 0 of `reserved`: developer knob, enables the scouting round
     a.no_windows = (o.reserved & 2) != 0;    // bit 1: developer knob, medium pairs skip the column-window stage
     a.test_small_windows = (o.reserved & 4) != 0;   // bit 2: honoured by emulator builds only
+    a.cta_fill = (o.reserved & 512) != 0;           // bit 9: developer knob, no grid-pipelined primary fill
     a.pair_major_wave = (o.reserved & 256) != 0;    // bit 8: developer knob, --no-ts strips in (pair, strip) ticket order
     a.fused_windows = (o.reserved & 32) != 0;       // bit 5: developer knob, first window stage through the fused jump kernel
     a.narrow_fill = (o.reserved & 128) != 0;        // bit 7: developer knob, one warp per pair in the primary fill whatever the length

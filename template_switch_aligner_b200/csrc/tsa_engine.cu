@@ -193,6 +193,8 @@ struct Engine::Impl {
     DevBuf ops, ops_off, ops_cap, ops_len, recs, n_recs, tstatus, rows, work_a, work_b, tables;
     DevBuf band, winflag;                             // column windows: band vectors of the fill, overflow flags
     DevBuf cpflag;                                    // ... and the chain-pair bitmaps of the long class
+    DevBuf fill_prog;                                 // grid-pipelined primary fill: progress counters per (pair, column block)
+    size_t fill_prog_ints = 0;
     size_t cpflag_ints = 0;
     DevBuf q_hdr, q_rows, q_counts;                   // row queue between the row kernel and the evaluation kernel
     size_t q_cap = 0;                                 // slots
@@ -287,7 +289,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     I.any_win = false;
     for (auto& l : I.class_list) l.clear();
     for (auto& v : I.class_maxlen) v = 0;
-    size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0, tab = 0, cpf_ints = 0;
+    size_t seq_bytes = 0, cells = 0, vec = 0, scr = 0, tab = 0, cpf_ints = 0, prog_ints = 0;
     I.max_m = 0; I.max_n = 0;
     I.wave_ck = false;
     if (!I.ts_enabled && opt.traceback && n > 0 && opt.wave_checkpoints >= 0) {
@@ -313,6 +315,12 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
         pm.scr = (long long)scr; scr += ((3 * ((size_t)pv.n + 1) + 1) & ~(size_t)1) * (wide_fill ? K1_WIDE_MAX : 1);
         pm.mat = (long long)cells;
         pm.tab = -1; pm.lw = 0; pm.cpf = -1; pm.cpf_words = 0;
+        pm.prog = (long long)prog_ints;
+#ifdef TSA_EMUL
+        if (I.ts_enabled) prog_ints += (size_t)pv.m + 2;                                   // (32-column blocks and narrower in the emulator tests)
+#else
+        if (I.ts_enabled) prog_ints += ((size_t)pv.m + 1 + 32 * K1_CB - 1) / (32 * K1_CB);
+#endif
         const int W = std::max(pv.n, pv.m) + 1;
         if (I.ts_enabled) {
             if (dev_.left_flank + dev_.right_flank + 1 >= KEY_PLANES) { I.status[i] = PAIR_ERR_FLANKS; continue; }
@@ -418,6 +426,8 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     if (I.ts_enabled) { I.D.ensure(cells * 2); I.DT.ensure(cells * 2); I.seedA.ensure(cells * 4); I.seedB.ensure(cells * 4); }
     if (I.any_win) { I.band.ensure(vec * 8); I.winflag.ensure(n * 4); I.cpflag.ensure(cpf_ints * 4 + 4); }
     I.cpflag_ints = cpf_ints;
+    I.fill_prog_ints = prog_ints;
+    if (prog_ints) I.fill_prog.ensure(prog_ints * 4);
     if (I.flank) { I.PA.ensure(cells * 6); I.PB.ensure(cells * 6); I.tgt_key.ensure(n * 4); I.best_plane.ensure(n * 4); }
     if (opt.traceback) {
         I.ops.ensure(I.ops_total); I.ops_off.ensure(n * 8); I.ops_cap.ensure(n * 4); I.ops_len.ensure(n * 4);
@@ -487,6 +497,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
     ck.band = I.any_win ? I.band.as<int>() : nullptr;
     ck.winflag = I.any_win ? I.winflag.as<int>() : nullptr;
     ck.cpflag = I.any_win && I.cpflag_ints ? I.cpflag.as<int>() : nullptr;
+    ck.fill_prog = I.fill_prog_ints ? I.fill_prog.as<int>() : nullptr;
     ck.win_stage = 0;
     ck.seeds_merged = 0;
     rt::stream_sync(I.stream);
@@ -541,11 +552,32 @@ void Engine::run_staged() {
             }
             TSA_LAUNCH(kern, dim3((unsigned)cnt), dim3(32 * warps), (size_t)(warps * K1_SMEM_INTS + 1) * sizeof(int), I.stream, ckm, d_list, cnt, layer);
         };
+        // One warp per column block over the whole device (very long pairs: a layer of one pair is otherwise filled by one SM)
+        auto grid_pipe = [&](auto kern, int cb) {
+            Chunk ckm = I.ck;
+            if (layer > 0 && !I.ck.pl_in) {
+                const int tiles = ((I.max_n + 32) / 32) * ((I.max_m + 32) / 32);
+                for (int off = 0; off < cnt; off += 65535) {
+                    const int c2 = std::min(65535, cnt - off);
+                    TSA_LAUNCH(k_merge_seeds, dim3((unsigned)std::min(tiles, 2048), (unsigned)c2), dim3(256), (size_t)32 * 33 * sizeof(int), I.stream, I.ck, d_list + off, c2);
+                    stats_.launches++;
+                }
+                ckm.seeds_merged = 1;
+            }
+            rt::dev_memset(I.fill_prog.p, 0, I.fill_prog_ints * 4, I.stream);
+            const int nb = (I.max_m + 1 + 32 * cb - 1) / (32 * cb);
+            for (int off = 0; off < cnt; off += 65535) {
+                const int c2 = std::min(65535, cnt - off);
+                TSA_LAUNCH(kern, dim3((unsigned)nb, (unsigned)c2), dim3(32), (size_t)(K1_SMEM_INTS + 1) * sizeof(int), I.stream, ckm, d_list + off, c2, layer);
+            }
+        };
 #ifdef TSA_EMUL
-        if ((I.opt.test_small_windows || I.opt.test_tiled) && I.ts_enabled && I.max_m + 1 > 32)   // CPU tests of the pipelined fill: 32-column blocks
-            wide(k_primary_fill<1, 4>, 4);
+        if ((I.opt.test_small_windows || I.opt.test_tiled) && I.ts_enabled && I.max_m + 1 > 128) grid_pipe(k_primary_fill<1, 0>, 1);   // CPU tests: 32-column blocks
+        else if ((I.opt.test_small_windows || I.opt.test_tiled) && I.ts_enabled && I.max_m + 1 > 32) wide(k_primary_fill<1, 4>, 4);
         else
 #endif
+        if (I.max_m + 1 > 32 * K1_CB * K1_WIDE_MAX && !I.opt.narrow_fill && !I.opt.cta_fill) grid_pipe(k_primary_fill<K1_CB, 0>, K1_CB);
+        else
         if (I.max_m + 1 <= 32 * 5) TSA_LAUNCH(k_primary_fill<5>, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
         else if (I.max_m + 1 > 32 * K1_CB * 4 && !I.opt.narrow_fill) wide(k_primary_fill<K1_CB, K1_WIDE_MAX>, K1_WIDE_MAX);
         else if (I.max_m + 1 > 32 * K1_CB && !I.opt.narrow_fill) wide(k_primary_fill<K1_CB, 4>, 4);
@@ -657,6 +689,7 @@ void Engine::run_staged() {
         stats_.chains_run += h[1]; stats_.rows_filled += h[2]; stats_.rows_jumped += h[3]; stats_.chains_started += h[4];
         if (getenv("TSA_B200_DEBUG")) fprintf(stderr, "[tsalign_b200] layer: chains %d/%d rows %d queued %d dominated %d evaluated %d\n", h[1], h[4], h[2], h[5], h[6], h[3]);
         for (int c = 0; c < N_CLASS; c++) counts8[c] = h[8 + c];
+        if (h[7]) throw std::runtime_error("primary fill: a column block waited for its left neighbour for too long");
     };
     // Row queue of the split jump (classes without column windows): sized from the learned demand per pair, at least the worst case
     // of one pair (every row of every chain queued), at most 6 GiB.

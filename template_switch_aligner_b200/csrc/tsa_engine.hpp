@@ -19,6 +19,7 @@ struct AlignOptions {
     bool no_windows = false;       // developer knob: pairs of 545..1055 characters skip the column-window stage (parity tests)
     int wave_checkpoints = 0;      // --no-ts with alignments: 0 = checkpoint rows + recomputed tiles for chunks of long pairs, codes of the whole
                                    // matrix otherwise; 1 = always checkpoints; -1 = never (developer knob, parity tests)
+    bool cta_fill = false;         // developer knob: very long pairs keep the one-CTA-per-pair primary fill (timing)
     bool pair_major_wave = false;  // developer knob: --no-ts strips handed out in (pair, strip) order instead of strip-major (timing)
     bool fused_windows = false;    // developer knob: the first window stage runs the fused jump kernel instead of row queue + evaluation (parity tests, timing)
     bool narrow_fill = false;      // developer knob: the primary fill of long pairs stays one warp per pair (parity tests, timing)

@@ -81,6 +81,7 @@ TSA_DEV int ffs_u32(uint32_t v) { return __ffs((int)v); }                       
 TSA_DEV int ld_acquire_s32(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 TSA_DEV void st_release_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 TSA_DEV int ld_cg_s32(const int* p) { return __ldcg(p); }
+TSA_DEV void thread_fence() { __threadfence(); }
 #ifndef TSA_SPIN_NS
 #define TSA_SPIN_NS 40
 #endif
@@ -200,6 +201,7 @@ inline int popc_u32(uint32_t v) { return __builtin_popcount(v); }
 inline int ld_acquire_s32(const int* p) { return *(const volatile int*)p; }
 inline void st_release_s32(int* p, int v) { *(volatile int*)p = v; }
 inline int ld_cg_s32(const int* p) { return *(const volatile int*)p; }
+inline void thread_fence() {}
 inline void spin_pause() { emu::spin_yield(); }   // lets the other warps of the block run
 }  // namespace tsa
 #endif

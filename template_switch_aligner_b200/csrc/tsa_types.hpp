@@ -63,6 +63,7 @@ struct PairMeta {
     int lw;                  // columns of one table row (32 * C of the pair's jump-kernel class; windowed pairs: the whole row, padded to 8)
     int win;                 // 1: the jump / traceback kernels run on column windows of this pair (k_ts_jump<C, true>)
     int cpf_words;           // words of one chain-pair bitmap (below)
+    long long prog;          // int offset of this pair's progress counters in Chunk::fill_prog (grid-pipelined primary fill), one per column block
     long long cpf;           // int offset of this pair's two chain-pair bitmaps in Chunk::cpflag (bit kind * n_ep + chain pair: the windows of
                              // that chain pair overflowed the first / the second window stage of this layer), -1: none (not the long class)
 };
@@ -133,6 +134,7 @@ struct Chunk {
                              // D < thr - min_ts (the only cells a template switch below the threshold can start from); null: unused
     int* winflag;            // [pair] bit 0: a chain's window did not fit the first-stage class in this layer (redo in the second
                              // stage); bit 1: it did not fit the widest class either (the pair is refused)
+    int* fill_prog;          // grid-pipelined primary fill: chunks finished per (pair, column block), zeroed before every launch
     int* cpflag;             // chain-pair bitmaps of the long class (PairMeta::cpf)
     int seeds_merged;        // 1: seedA already holds min(seedA, seedB transposed) (k_merge_seeds): the primary fill reads seedA only
     int win_stage;           // 0: not a windowed launch; 1: first stage; 2: second stage (only pairs with bit 0 set)
