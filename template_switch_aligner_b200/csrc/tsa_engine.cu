@@ -319,7 +319,7 @@ bool Engine::stage(const PairView* pairs, size_t n, const AlignOptions& opt) {
 #ifdef TSA_EMUL
         if (I.ts_enabled) prog_ints += (size_t)pv.m + 2;                                   // (32-column blocks and narrower in the emulator tests)
 #else
-        if (I.ts_enabled) prog_ints += ((size_t)pv.m + 1 + 32 * K1_CB - 1) / (32 * K1_CB);
+        if (I.ts_enabled) prog_ints += ((size_t)pv.m + 1 + 32 * K1_GRID_CB - 1) / (32 * K1_GRID_CB);
 #endif
         const int W = std::max(pv.n, pv.m) + 1;
         if (I.ts_enabled) {
@@ -576,7 +576,7 @@ void Engine::run_staged() {
         else if ((I.opt.test_small_windows || I.opt.test_tiled) && I.ts_enabled && I.max_m + 1 > 32) wide(k_primary_fill<1, 4>, 4);
         else
 #endif
-        if (I.max_m + 1 > 32 * K1_CB * K1_WIDE_MAX && !I.opt.narrow_fill && !I.opt.cta_fill) grid_pipe(k_primary_fill<K1_CB, 0>, K1_CB);
+        if (I.max_m + 1 > 32 * K1_CB * K1_WIDE_MAX && !I.opt.narrow_fill && !I.opt.cta_fill) grid_pipe(k_primary_fill<K1_GRID_CB, 0>, K1_GRID_CB);
         else
         if (I.max_m + 1 <= 32 * 5) TSA_LAUNCH(k_primary_fill<5>, dim3((unsigned)((cnt + K1_WARPS - 1) / K1_WARPS)), dim3(32 * K1_WARPS), k1_smem, I.stream, I.ck, d_list, cnt, layer);
         else if (I.max_m + 1 > 32 * K1_CB * 4 && !I.opt.narrow_fill) wide(k_primary_fill<K1_CB, K1_WIDE_MAX>, K1_WIDE_MAX);
